@@ -1,0 +1,158 @@
+/* vpb200.h -- C ABI of the B200-native speaker-embedding extraction path (sm_100a).
+ *
+ * The reference (yeyupiaoling/VoiceprintRecognition-Pytorch, mvector 1.1.1) is pure Python and has NO FFI /
+ * plugin boundary; the seam it offers is two Python callables:
+ *     seam 1  AudioFeaturizer.forward(waveforms[, lens_ratio]) -> [B,T,F]   mvector/data_utils/featurizer.py:53-91
+ *     seam 2  predictor(features) -> [B, embd_dim]                          mvector/predict.py:228,262
+ * driven by MVectorPredictor.predict / predict_batch (mvector/predict.py:214-265).  This header is the C ABI a
+ * maintainer binds (ctypes stub in INTEGRATION.md) to replace exactly those two callables:
+ *     vp_fbank / vp_melspec   <-> seam 1 (KaldiFbank: featurizer.py:119-132 -> torchaudio kaldi.py:514-645;
+ *                                          MelSpectrogram: featurizer.py:41-42,76; CMN + mask: featurizer.py:77-90)
+ *     vp_embed                <-> seam 2 (nn.Sequential(build_model(...)).eval(), predict.py:54-63)
+ *     vp_embed_wave           <-> seam 1 + seam 2 back to back (predict.py:256-262)
+ *
+ * Conventions: all tensor arguments are caller-owned DEVICE pointers to float32 (row-major, dense); every call
+ * takes the CUDA stream to enqueue on (a cudaStream_t passed as void*, NULL = legacy default stream) and is
+ * asynchronous; functions return 0 on success or a VP_ERR_* code, with vp_last_error() giving the message.
+ * No hidden device allocation after vp_program_create.  One handle per device; thread-compatible (one
+ * thread/stream at a time per handle / program).  There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef VPB200_H_
+#define VPB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VP_ABI_VERSION 1
+
+enum {
+  VP_OK = 0,
+  VP_ERR_INVALID = 1,      /* bad argument / inconsistent op */
+  VP_ERR_CUDA = 2,         /* a CUDA runtime call failed (message has the cudaError string) */
+  VP_ERR_NOMEM = 3,
+  VP_ERR_UNSUPPORTED = 4   /* shape/option outside what the kernels implement; never silently emulated */
+};
+
+typedef struct vp_handle vp_handle;
+typedef struct vp_program vp_program;
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Front-end (seam 1).  kind 0 = Kaldi Fbank framing (snip_edges, per-frame DC removal, pre-emphasis, window,
+ * zero-pad to n_fft; kaldi.py:154-217), kind 1 = torch.stft framing (reflect-centred frames of n_fft samples,
+ * functional.py:123-135).  Then |rFFT|^2 (power 2) or |rFFT| (power 1), sparse triangular mel projection,
+ * optional log(max(x, log_floor)), then (featurizer.py:77-90) time-mean subtraction over ALL T frames and zeroing
+ * of frames >= keep_frames[b].
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct vp_frontend_desc {
+  int32_t kind;         /* 0 kaldi-fbank framing, 1 centred-STFT framing */
+  int32_t n_fft;        /* FFT size, power of two in [256, 2048] */
+  int32_t win_length;   /* samples taken per frame (<= n_fft); window[] has this many taps */
+  int32_t hop;          /* frame shift in samples */
+  int32_t n_mels;       /* output feature dimension F (<= 128) */
+  int32_t remove_dc;    /* kind 0: subtract the frame mean */
+  float   preemph;      /* kind 0: pre-emphasis coefficient (0 = off) */
+  int32_t power;        /* 2 = power spectrum, 1 = magnitude */
+  int32_t use_log;      /* 1: log(max(mel, log_floor)) */
+  float   log_floor;
+} vp_frontend_desc;
+
+int vp_create(int device, vp_handle** out);
+void vp_destroy(vp_handle* h);
+const char* vp_last_error(const vp_handle* h);
+int vp_abi_version(void);
+int32_t vp_sizeof_op(void);             /* binding self-check: sizeof(vp_op) */
+int32_t vp_sizeof_frontend_desc(void);  /* binding self-check: sizeof(vp_frontend_desc) */
+
+/* window: win_length floats.  Mel bank in CSR-like form: filter m covers FFT bins
+ * [mel_start[m], mel_start[m] + mel_count[m]) with weights mel_w[mel_off[m] ...]; all host pointers, copied. */
+int vp_frontend_set(vp_handle* h, const vp_frontend_desc* desc, const float* window, const int32_t* mel_start,
+                    const int32_t* mel_count, const int32_t* mel_off, const float* mel_w, int32_t n_w);
+/* number of frames T the configured front-end yields for n_samples (kaldi.py:63-67 / torch.stft) */
+int32_t vp_num_frames(const vp_handle* h, int32_t n_samples);
+
+/* wave [B, Lpad] (zero padded to the batch max, predict.py:248-254) -> feats [B, T, F], T = vp_num_frames(Lpad).
+ * keep_frames: device int32 [B] = round(len_i / Lmax * T) (featurizer.py:82-84) or NULL for no masking.
+ * scratch: device floats, at least vp_frontend_scratch_floats(B, Lpad).  vp_fbank requires kind 0, vp_melspec kind 1. */
+size_t vp_frontend_scratch_floats(const vp_handle* h, int32_t B, int32_t Lpad);
+int vp_fbank(vp_handle* h, const float* wave, int32_t B, int32_t Lpad, const int32_t* keep_frames, float* feats,
+             float* scratch, void* stream);
+int vp_melspec(vp_handle* h, const float* wave, int32_t B, int32_t Lpad, const int32_t* keep_frames, float* feats,
+               float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Backbone (seam 2).  The host (Python mirror of mvector/models/*.py) lowers a model + a concrete (B, T) to a
+ * straight-line program of fused ops over a workspace arena; weights live in one packed arena uploaded once.
+ * Activations are channel-last: 1-D maps are [B, T, C], 2-D maps are [B, T, F, C] (T = time = conv2d W axis,
+ * F = frequency = conv2d H axis of the reference's [B, C, F, T]).
+ * ---------------------------------------------------------------------------------------------------------- */
+enum {                       /* vp_op.kind */
+  VP_OP_CONV = 1,            /* implicit-GEMM conv1d/conv2d/linear with fused prologue + epilogue */
+  VP_OP_CONV_C1 = 2,         /* 3x3 conv2d with Cin = 1 on the feature map [B,T,F] -> [B,T,F,C] */
+  VP_OP_COLSTATS = 3,        /* per-utterance column statistics over rows (mean / mean+std variants / segments) */
+  VP_OP_ASP_POOL = 4,        /* softmax over T of logits, attentive mean + std (pooling.py:122-126) */
+  VP_OP_EW = 5               /* elementwise: gate*x + residual, AFF blend, copy */
+};
+enum { VP_ACT_NONE = 0, VP_ACT_RELU = 1, VP_ACT_HARDTANH20 = 2, VP_ACT_SIGMOID = 3, VP_ACT_TANH = 4, VP_ACT_SILU = 5 };
+enum { VP_PAD_ZERO = 0, VP_PAD_REFLECT = 1 };
+enum { VP_SRC2_NONE = 0, VP_SRC2_ADD = 1, VP_SRC2_CONCAT = 2 };
+enum {                       /* VP_OP_COLSTATS modes (op.mode) */
+  VP_STATS_MEAN = 0,               /* out[b, c] = mean over rows                                  (ecapa_tdnn.py:79, resnet_se.py:58-60) */
+  VP_STATS_MEAN_STD_CLAMP = 1,     /* [mean ; sqrt(clamp(sum((x-mean)^2)/R, eps))]                (pooling.py:91-94,108) */
+  VP_STATS_MEAN_STD_UNBIASED = 2,  /* [mean ; sqrt(sum((x-mean)^2)/(R-1))]                        (campplus.py:27-33) */
+  VP_STATS_MEAN_STD_TSTP = 3,      /* [mean ; sqrt(sum((x-mean)^2)/(R-1) + eps)]                  (pooling.py:140-148) */
+  VP_STATS_SEG_CONTEXT = 4         /* out[b, s, c] = mean over rows + mean over segment s (ceil)  (campplus.py:96-111) */
+};
+enum { VP_EW_GATE_RES = 0, VP_EW_AFF = 1, VP_EW_COPY = 2 };
+enum { VP_BUF_NONE = -1, VP_BUF_INPUT = -2, VP_BUF_OUTPUT = -3 };  /* special values for activation offsets */
+enum { VP_ENGINE_AUTO = 0, VP_ENGINE_FFMA = 1, VP_ENGINE_TC = 2 }; /* vp_op.engine: which conv kernel family */
+
+typedef struct vp_op {
+  int32_t kind;
+  int32_t mode;            /* COLSTATS / EW sub-mode */
+  int32_t engine;          /* VP_OP_CONV: VP_ENGINE_* */
+  int32_t B;               /* utterances */
+  /* activation operands: byte offsets into the program workspace, or VP_BUF_* */
+  int64_t src, src2, dst, res, gate, ubias;
+  /* weight-arena operands: byte offsets (or -1) */
+  int64_t w, bias, pre_s, pre_h, post_s, post_h;
+  /* source geometry: rows = B*Tin*Fin, each row in_ld floats, channels [in_coff, in_coff+Cin) */
+  int32_t Tin, Fin, Cin, in_ld, in_coff;
+  int32_t src2_mode, src2_ld, src2_coff, Cin2;   /* ADD: same Cin; CONCAT: channels Cin..Cin+Cin2 come from src2 */
+  /* destination geometry: rows = B*Tout*Fout, row out_ld floats, channels [out_coff, out_coff+Cout) */
+  int32_t Tout, Fout, Cout, out_ld, out_coff;
+  int32_t res_ld, res_coff;
+  /* taps (time, freq), strides, dilations, paddings */
+  int32_t KT, KF, sT, sF, dT, dF, padT, padF, pad_mode;
+  int32_t w_ld;            /* floats per weight row; weight element (n, (kt*KF+kf)*CinTot + ci) */
+  int32_t pre_relu;        /* prologue: a = relu(a*pre_s[ci] + pre_h[ci]) when pre_s >= 0 (campplus.py:141-149) */
+  int32_t act, act2;       /* y = act2(act(acc + bias + ubias) * post_s + post_h) * gate + res)  -- see DESIGN.md */
+  int32_t seg_len, n_seg;  /* gate / ubias / SEG_CONTEXT rows per utterance: row (b*n_seg + min(t/seg_len, n_seg-1)) */
+  float   eps;
+  int32_t reserved[7];
+} vp_op;
+
+/* Upload the packed fp32 weight arena (host pointer, copied to the device; replaces any previous arena). */
+int vp_weights_load(vp_handle* h, const void* host_blob, size_t nbytes);
+
+/* Validate + own a program for fixed (B, T): allocates workspace_bytes of device memory once. */
+int vp_program_create(vp_handle* h, const vp_op* ops, int32_t n_ops, size_t workspace_bytes, size_t input_floats,
+                      size_t output_floats, vp_program** out);
+void vp_program_destroy(vp_program* p);
+/* feats [B,T,F] -> emb [B, embd_dim] */
+int vp_embed(vp_program* p, const float* feats, float* emb, void* stream);
+/* wave [B,Lpad] -> emb: front-end then program; feats_scratch holds B*T*F floats, fe_scratch as for vp_fbank */
+int vp_embed_wave(vp_program* p, const float* wave, int32_t B, int32_t Lpad, const int32_t* keep_frames,
+                  float* feats_scratch, float* fe_scratch, float* emb, void* stream);
+/* number of kernel launches one vp_embed enqueues (bench.py's gpu_launches) */
+int32_t vp_program_launches(const vp_program* p);
+/* debugging / tests: copy a workspace region to a caller device buffer on the stream */
+int vp_program_peek(vp_program* p, int64_t byte_offset, size_t nbytes, void* dst_device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPB200_H_ */

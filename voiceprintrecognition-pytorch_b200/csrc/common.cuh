@@ -1,0 +1,123 @@
+// Shared device helpers and kernel parameter blocks for the vpb200 library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/vpb200.h"
+
+namespace vpb {
+
+// Resolved (device-pointer) form of a vp_op, passed to kernels by value.
+struct ConvParams {
+  const float* src; const float* src2; float* dst; const float* res; const float* gate; const float* ubias;
+  const float* w; const float* bias; const float* pre_s; const float* pre_h; const float* post_s; const float* post_h;
+  int M, N, K;                       // M = B*Tout*Fout rows, N = Cout, K = KT*KF*CinTot
+  int B, Tin, Fin, Cin, CinTot, in_ld, in_coff;
+  int src2_mode, src2_ld, src2_coff;
+  int Tout, Fout, out_ld, out_coff, res_ld, res_coff;
+  int KT, KF, sT, sF, dT, dF, padT, padF, pad_mode;
+  int w_ld, pre_relu, act, act2, seg_len, n_seg;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case VP_ACT_RELU: return fmaxf(v, 0.f);
+    case VP_ACT_HARDTANH20: return fminf(fmaxf(v, 0.f), 20.f);
+    case VP_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case VP_ACT_TANH: return tanhf(v);
+    case VP_ACT_SILU: return v / (1.f + expf(-v));
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Decoded A-operand row (one output position): where its receptive field starts in the source map.
+struct RowInfo {
+  int base;   // b * Tin * Fin (row index of the utterance's first source row)
+  int t0;     // to*sT - padT
+  int f0;     // fo*sF - padF
+  int valid;  // m < M
+};
+
+__device__ __forceinline__ RowInfo decode_row(const ConvParams& p, int m) {
+  RowInfo r;
+  r.valid = m < p.M;
+  int mm = r.valid ? m : 0;
+  int per = p.Tout * p.Fout;
+  int b = mm / per;
+  int rem = mm - b * per;
+  int to = rem / p.Fout;
+  int fo = rem - to * p.Fout;
+  r.base = b * p.Tin * p.Fin;
+  r.t0 = to * p.sT - p.padT;
+  r.f0 = fo * p.sF - p.padF;
+  return r;
+}
+
+// Gather 4 consecutive K elements (one tap, 4 channels) of the implicit-GEMM A operand, with zero / reflect padding,
+// optional second source (add / channel-concat) and optional per-channel affine(+ReLU) prologue.
+// k must be a multiple of 4; Cin, CinTot, in_ld, in_coff (and the src2 equivalents) multiples of 4.
+__device__ __forceinline__ float4 gather_a4(const ConvParams& p, const RowInfo& r, int k) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!r.valid || k >= p.K) return v;
+  int tap = k / p.CinTot;
+  int ci = k - tap * p.CinTot;
+  int kt = tap / p.KF;
+  int kf = tap - kt * p.KF;
+  int ti = r.t0 + kt * p.dT;
+  int fi = r.f0 + kf * p.dF;
+  if (p.pad_mode == VP_PAD_REFLECT) {
+    if (ti < 0) ti = -ti;
+    if (ti >= p.Tin) ti = 2 * (p.Tin - 1) - ti;
+  }
+  if (ti < 0 || ti >= p.Tin || fi < 0 || fi >= p.Fin) return v;
+  size_t row = (size_t)r.base + (size_t)ti * p.Fin + fi;
+  if (p.src2_mode == VP_SRC2_CONCAT && ci >= p.Cin) {
+    v = __ldg(reinterpret_cast<const float4*>(p.src2 + row * p.src2_ld + p.src2_coff + (ci - p.Cin)));
+  } else {
+    v = __ldg(reinterpret_cast<const float4*>(p.src + row * p.in_ld + p.in_coff + ci));
+    if (p.src2_mode == VP_SRC2_ADD) {
+      float4 u = __ldg(reinterpret_cast<const float4*>(p.src2 + row * p.src2_ld + p.src2_coff + ci));
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+  }
+  if (p.pre_s != nullptr) {
+    float4 s = __ldg(reinterpret_cast<const float4*>(p.pre_s + ci));
+    float4 h = __ldg(reinterpret_cast<const float4*>(p.pre_h + ci));
+    v.x = fmaf(v.x, s.x, h.x); v.y = fmaf(v.y, s.y, h.y); v.z = fmaf(v.z, s.z, h.z); v.w = fmaf(v.w, s.w, h.w);
+    if (p.pre_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+  }
+  return v;
+}
+
+// Fused epilogue for one output element (row m, column n); urow = per-utterance(/segment) row for ubias & gate.
+__device__ __forceinline__ float epilogue1(const ConvParams& p, float acc, int m, int n, int urow) {
+  float v = acc;
+  if (p.bias) v += __ldg(p.bias + n);
+  if (p.ubias) v += __ldg(p.ubias + (size_t)urow * p.N + n);
+  v = apply_act(v, p.act);
+  if (p.post_s) v = fmaf(v, __ldg(p.post_s + n), __ldg(p.post_h + n));
+  if (p.gate) v *= __ldg(p.gate + (size_t)urow * p.N + n);
+  if (p.res) v += __ldg(p.res + (size_t)m * p.res_ld + p.res_coff + n);
+  return apply_act(v, p.act2);
+}
+
+__device__ __forceinline__ int urow_of(const ConvParams& p, int m) {
+  int per = p.Tout * p.Fout;
+  int b = m / per;
+  int to = (m - b * per) / p.Fout;
+  int s = to / p.seg_len;
+  if (s >= p.n_seg) s = p.n_seg - 1;
+  return b * p.n_seg + s;
+}
+
+}  // namespace vpb

@@ -1,0 +1,203 @@
+// Exact-fp32 implicit-GEMM convolution (FFMA pipe) with fused gather prologue and epilogue.
+//
+// Replaces, per layer, the reference's  F.pad(reflect) -> nn.Conv1d/Conv2d -> ReLU/BN/...  op chains
+// (mvector/models/utils.py:39-138, campplus.py:41-111,219-255, resnet_se.py:23-44, eres2net.py:85-108) with ONE kernel:
+//   out[m, n] = epi( sum_k A(m, k) * W[n, k] ),  m = (b, to, fo), k = (kt, kf, ci)
+// A is gathered on the fly from the channel-last activation map (no im2col / no padded copy / no concat copy).
+// This is the bit-faithful fp32 engine: used for layers that are not tensor-core shaped (small N/K, tiny M) and as the
+// on-device cross-check of the tcgen05 engine (conv_tc.cu).
+//
+// Tiling: CTA = 256 threads, 128 (M) x BN (N) x 16 (K) tiles, register-prefetch double buffering, 8 x TN micro-tile.
+#include "kernels.cuh"
+
+namespace vpb {
+
+constexpr int BM = 128;
+constexpr int BK = 16;
+constexpr int LDS_PAD = 4;
+
+template <int BN>
+__global__ void __launch_bounds__(256, 2) conv_ffma_kernel(const __grid_constant__ ConvParams p) {
+  constexpr int TN = BN / 16;           // columns per thread: 8, 4 or 2
+  constexpr int LDA = BM + LDS_PAD;
+  constexpr int LDB = BN + LDS_PAD;
+  __shared__ __align__(16) float As[2][BK][LDA];
+  __shared__ __align__(16) float Bs[2][BK][LDB];
+
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  // ---- loader mapping: 4 lanes cover one row's 16 K-floats (64 B) ----
+  const int kq = tid & 3;
+  const int lr = tid >> 2;              // 0..63
+  RowInfo rowA0 = decode_row(p, m0 + lr);
+  RowInfo rowA1 = decode_row(p, m0 + lr + 64);
+  constexpr int B_LOADS = (BN >= 128) ? 2 : 1;
+  const bool b_active = (BN >= 64) || (lr < BN);
+
+  float4 ra0, ra1, rb[B_LOADS];
+  auto load_tiles = [&](int k0) {
+    int k = k0 + kq * 4;
+    ra0 = gather_a4(p, rowA0, k);
+    ra1 = gather_a4(p, rowA1, k);
+#pragma unroll
+    for (int i = 0; i < B_LOADS; ++i) {
+      int n = n0 + lr + i * 64;
+      rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b_active && n < p.N && k < p.K)
+        rb[i] = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)n * p.w_ld + k));
+    }
+  };
+  auto store_tiles = [&](int buf) {
+    float* a = &As[buf][kq * 4][0];
+    a[0 * LDA + lr] = ra0.x; a[1 * LDA + lr] = ra0.y; a[2 * LDA + lr] = ra0.z; a[3 * LDA + lr] = ra0.w;
+    a[0 * LDA + lr + 64] = ra1.x; a[1 * LDA + lr + 64] = ra1.y; a[2 * LDA + lr + 64] = ra1.z; a[3 * LDA + lr + 64] = ra1.w;
+    if (b_active) {
+      float* b = &Bs[buf][kq * 4][0];
+#pragma unroll
+      for (int i = 0; i < B_LOADS; ++i) {
+        b[0 * LDB + lr + i * 64] = rb[i].x; b[1 * LDB + lr + i * 64] = rb[i].y;
+        b[2 * LDB + lr + i * 64] = rb[i].z; b[3 * LDB + lr + i * 64] = rb[i].w;
+      }
+    }
+  };
+
+  // ---- compute mapping: 16 x 16 threads, rows {ty*4..+3, 64+ty*4..+3}, cols per TN ----
+  const int tx = tid & 15;
+  const int ty = tid >> 4;
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int nk = (p.K + BK - 1) / BK;
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[8], b[TN];
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      if constexpr (TN == 8) {
+        float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+        float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+      } else if constexpr (TN == 4) {
+        float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+      } else {
+        float2 b0 = *reinterpret_cast<const float2*>(&Bs[buf][k][tx * 2]);
+        b[0] = b0.x; b[1] = b0.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // ---- fused epilogue ----
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= p.M) continue;
+    const int urow = urow_of(p, m);
+    float* orow = p.dst + (size_t)m * p.out_ld + p.out_coff;
+    if constexpr (TN == 8) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int n = n0 + h * 64 + tx * 4;
+        if (n + 3 < p.N) {
+          float4 o;
+          o.x = epilogue1(p, acc[i][h * 4 + 0], m, n + 0, urow);
+          o.y = epilogue1(p, acc[i][h * 4 + 1], m, n + 1, urow);
+          o.z = epilogue1(p, acc[i][h * 4 + 2], m, n + 2, urow);
+          o.w = epilogue1(p, acc[i][h * 4 + 3], m, n + 3, urow);
+          *reinterpret_cast<float4*>(orow + n) = o;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n + j < p.N) orow[n + j] = epilogue1(p, acc[i][h * 4 + j], m, n + j, urow);
+        }
+      }
+    } else {
+      const int n = n0 + tx * TN;
+#pragma unroll
+      for (int j = 0; j < TN; ++j)
+        if (n + j < p.N) orow[n + j] = epilogue1(p, acc[i][j], m, n + j, urow);
+    }
+  }
+}
+
+cudaError_t launch_conv_ffma(const ConvParams& p, cudaStream_t stream) {
+  dim3 block(256);
+  if (p.N > 64) {
+    dim3 grid((p.M + BM - 1) / BM, (p.N + 127) / 128);
+    conv_ffma_kernel<128><<<grid, block, 0, stream>>>(p);
+  } else if (p.N > 32) {
+    dim3 grid((p.M + BM - 1) / BM, 1);
+    conv_ffma_kernel<64><<<grid, block, 0, stream>>>(p);
+  } else {
+    dim3 grid((p.M + BM - 1) / BM, 1);
+    conv_ffma_kernel<32><<<grid, block, 0, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3x3 conv2d with a single input channel on the feature map (the stem of the 2-D backbones):
+//   F.relu(bn1(conv1(x.unsqueeze(1))))  campplus.py:284, resnet_se.py:131-133, eres2net.py:243
+// in: feats [B, T, F] (one channel), out: [B, T, F, C] channel-last.  w: [C][kt][kf] (BN folded by the host), bias [C].
+// One thread per (b, t, f) position x 4 output channels; 9 taps cached in registers.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_c1_kernel(const __grid_constant__ ConvParams p) {
+  const int groups = p.N >> 2;
+  const long long total = (long long)p.M * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    const int m = (int)(idx / groups);
+    RowInfo r = decode_row(p, m);
+    float x[9];
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+      for (int kf = 0; kf < 3; ++kf) {
+        int ti = r.t0 + kt, fi = r.f0 + kf;
+        bool ok = ti >= 0 && ti < p.Tin && fi >= 0 && fi < p.Fin;
+        x[kt * 3 + kf] = ok ? __ldg(p.src + ((size_t)r.base + (size_t)ti * p.Fin + fi) * p.in_ld + p.in_coff) : 0.f;
+      }
+    float o[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int n = g * 4 + c;
+      const float* wr = p.w + (size_t)n * p.w_ld;
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) a = fmaf(x[k], __ldg(wr + k), a);
+      o[c] = epilogue1(p, a, m, n, urow_of(p, m));
+    }
+    *reinterpret_cast<float4*>(p.dst + (size_t)m * p.out_ld + p.out_coff + g * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+cudaError_t launch_conv_c1(const ConvParams& p, cudaStream_t stream) {
+  long long total = (long long)p.M * (p.N >> 2);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  conv_c1_kernel<<<blocks, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace vpb

@@ -1,0 +1,234 @@
+// Fused front-end: framing -> (DC removal, pre-emphasis) -> window -> real FFT -> power -> sparse mel -> log,
+// one kernel, waveform read once from HBM through a shared-memory stage; then CMN + length mask.
+//
+// Replaces the reference's per-utterance Python loop over torchaudio.compliance.kaldi.fbank
+// (mvector/data_utils/featurizer.py:119-132 -> kaldi.py:514-645: ~250 ATen ops per utterance, window and mel bank
+// rebuilt on every call) and torchaudio.transforms.MelSpectrogram (featurizer.py:41-42,76), followed by
+// AudioFeaturizer.forward's transpose / mean-subtract / mask (featurizer.py:77-90).
+//
+// FFT: two real frames are packed into one complex length-N Stockham autosort FFT (radix-4 passes + one radix-2
+// pass when log2(N) is odd) held in shared memory; N/4 threads (<= 256) cooperate on one FFT.  Twiddles come from a
+// host-computed (fp64 -> fp32) table.  Bound: the algorithmic traffic is 4*L + 4*T*F bytes per utterance (HBM), the
+// kernel itself is shared-memory / issue bound.
+#include "kernels.cuh"
+
+namespace vpb {
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+__global__ void __launch_bounds__(256) frontend_kernel(const __grid_constant__ FrontendParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int N = p.N, WL = p.WL, F = p.F;
+  const int G = (N / 4 < 256) ? N / 4 : 256;        // threads per FFT
+  const int NG = 256 / G;                           // concurrent FFTs per CTA
+  const int span = (p.fpb - 1) * p.hop + WL;
+
+  float* stage = smem;                                              // span floats (rounded up to x4)
+  float* win = stage + ((span + 3) & ~3);                           // WL
+  float2* tw = reinterpret_cast<float2*>(win + ((WL + 3) & ~3));    // N
+  float2* bufA = tw + N;                                            // NG * N
+  float2* bufB = bufA + NG * N;                                     // NG * N
+  float* means = reinterpret_cast<float*>(bufB + NG * N);           // NG * 2
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int f0 = blockIdx.x * p.fpb;
+  const int g = tid / G;
+  const int t = tid - g * G;
+  const float* wv = p.wave + (size_t)b * p.L;
+
+  // ---- stage the waveform span, window and twiddles ----
+  const int q0 = f0 * p.hop;
+  for (int i = tid; i < span; i += 256) {
+    int s = q0 + i;
+    float v = 0.f;
+    if (p.kind == 1) {                      // torch.stft(center=True, pad_mode='reflect'): functional.py:123-135
+      s -= N / 2;
+      if (s < 0) s = -s;
+      if (s >= p.L) s = 2 * (p.L - 1) - s;
+      if (s >= 0 && s < p.L) v = __ldg(wv + s);
+    } else if (s < p.L) {
+      v = __ldg(wv + s);
+    }
+    stage[i] = v;
+  }
+  for (int i = tid; i < WL; i += 256) win[i] = __ldg(p.window + i);
+  for (int i = tid; i < N; i += 256) tw[i] = __ldg(p.twiddle + i);
+  __syncthreads();
+
+  const int iters = p.fpb / (2 * NG);
+  for (int it = 0; it < iters; ++it) {
+    const int fa = f0 + (it * NG + g) * 2;          // frames packed as real (fa) and imaginary (fa + 1) parts
+    const int oa = (fa - f0) * p.hop;
+    const bool va = fa < p.T, vb = fa + 1 < p.T;
+
+    // ---- per-frame mean (kaldi.py:183-186), one warp per frame ----
+    if (p.kind == 0 && p.remove_dc) {
+      const int w = t >> 5, lane = t & 31;
+      if (w < 2) {
+        const int o = oa + w * p.hop;
+        float s = 0.f;
+        if (w == 0 ? va : vb)
+          for (int j = lane; j < WL; j += 32) s += stage[o + j];
+        s = warp_sum(s);
+        if (lane == 0) means[g * 2 + w] = s / (float)WL;
+      }
+    }
+    __syncthreads();
+    float2* src = bufA + g * N;
+    float2* dst = bufB + g * N;
+    {
+      float ma = 0.f, mb = 0.f;
+      if (p.kind == 0 && p.remove_dc) { ma = means[g * 2]; mb = means[g * 2 + 1]; }
+      for (int j = t; j < N; j += G) {
+        float ya = 0.f, yb = 0.f;
+        if (j < WL) {
+          const int jp = j > 0 ? j - 1 : 0;
+          const float wj = win[j];
+          if (va) {
+            float x = stage[oa + j];
+            if (p.kind == 0) {
+              x = __fsub_rn(x, ma);
+              if (p.preemph != 0.f) x = __fsub_rn(x, __fmul_rn(p.preemph, __fsub_rn(stage[oa + jp], ma)));
+            }
+            ya = __fmul_rn(x, wj);
+          }
+          if (vb) {
+            float x = stage[oa + p.hop + j];
+            if (p.kind == 0) {
+              x = __fsub_rn(x, mb);
+              if (p.preemph != 0.f) x = __fsub_rn(x, __fmul_rn(p.preemph, __fsub_rn(stage[oa + p.hop + jp], mb)));
+            }
+            yb = __fmul_rn(x, wj);
+          }
+        }
+        src[j] = make_float2(ya, yb);
+      }
+    }
+    __syncthreads();
+
+    // ---- Stockham autosort FFT, radix 4 (+ one radix-2 pass) ----
+    for (int Ns = 1; Ns < N;) {
+      const int R = ((N / Ns) % 4 == 0) ? 4 : 2;
+      const int step = N / (Ns * R);
+      if (R == 4) {
+        const int q = N >> 2;
+        for (int j = t; j < q; j += G) {
+          const int kk = j & (Ns - 1);
+          float2 v0 = src[j], v1 = src[j + q], v2 = src[j + 2 * q], v3 = src[j + 3 * q];
+          if (Ns > 1) {
+            v1 = cmul(v1, tw[kk * step]);
+            v2 = cmul(v2, tw[2 * kk * step]);
+            v3 = cmul(v3, tw[3 * kk * step]);
+          }
+          const float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y);
+          const float2 a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
+          const float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
+          const float2 a3 = make_float2(v1.y - v3.y, -(v1.x - v3.x));      // (v1 - v3) * (-i)
+          const int base = (j - kk) * 4 + kk;
+          dst[base] = make_float2(a0.x + a2.x, a0.y + a2.y);
+          dst[base + Ns] = make_float2(a1.x + a3.x, a1.y + a3.y);
+          dst[base + 2 * Ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
+          dst[base + 3 * Ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
+        }
+      } else {
+        const int q = N >> 1;
+        for (int j = t; j < q; j += G) {
+          const int kk = j & (Ns - 1);
+          float2 v0 = src[j], v1 = cmul(src[j + q], tw[kk * step]);
+          const int base = (j - kk) * 2 + kk;
+          dst[base] = make_float2(v0.x + v1.x, v0.y + v1.y);
+          dst[base + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
+        }
+      }
+      __syncthreads();
+      float2* tmp = src; src = dst; dst = tmp;
+      Ns *= R;
+    }
+
+    // ---- split the packed spectrum, power (kaldi.py:616-618) into P[2][N/2+1] (reuses the idle FFT buffer) ----
+    const int NB = N / 2 + 1;
+    float* P = reinterpret_cast<float*>(dst);
+    for (int k = t; k < NB; k += G) {
+      const float2 z = src[k];
+      const float2 zn = src[(N - k) & (N - 1)];
+      const float ar = 0.5f * (z.x + zn.x), ai = 0.5f * (z.y - zn.y);
+      const float br = 0.5f * (z.y + zn.y), bi = -0.5f * (z.x - zn.x);
+      float pa = ar * ar + ai * ai, pb = br * br + bi * bi;
+      if (p.power == 1) { pa = sqrtf(pa); pb = sqrtf(pb); }
+      P[k] = pa;
+      P[NB + k] = pb;
+    }
+    __syncthreads();
+
+    // ---- sparse triangular mel projection + log floor (kaldi.py:630-633) ----
+    for (int idx = t; idx < 2 * F; idx += G) {
+      const int fr = idx / F;
+      const int m = idx - fr * F;
+      const int f = fa + fr;
+      if (f < p.T) {
+        const int st = __ldg(p.mel_start + m), cnt = __ldg(p.mel_count + m), off = __ldg(p.mel_off + m);
+        const float* pp = P + fr * NB + st;
+        float s = 0.f;
+        for (int i = 0; i < cnt; ++i) s = fmaf(pp[i], __ldg(p.mel_w + off + i), s);
+        if (p.use_log) s = logf(fmaxf(s, p.log_floor));
+        p.feats[((size_t)b * p.T + f) * F + m] = s;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- per-CTA column sums for the CMN mean (featurizer.py:79), fixed summation order ----
+  for (int m = tid; m < F; m += 256) {
+    float s = 0.f;
+    for (int f = f0; f < f0 + p.fpb && f < p.T; ++f) s += p.feats[((size_t)b * p.T + f) * F + m];
+    p.partial[((size_t)b * p.nblk + blockIdx.x) * F + m] = s;
+  }
+}
+
+// feats[b, t, :] -= mean_t(feats[b]) over ALL T frames, then frames t >= keep[b] are zeroed (featurizer.py:79-90).
+__global__ void __launch_bounds__(128) cmn_mask_kernel(float* feats, const float* partial, const int* keep, int T, int F,
+                                                       int nblk, int rows_per_cta) {
+  const int b = blockIdx.y;
+  const int m = threadIdx.x;
+  if (m >= F) return;
+  float s = 0.f;
+  for (int i = 0; i < nblk; ++i) s += partial[((size_t)b * nblk + i) * F + m];
+  const float mean = s / (float)T;
+  const int kp = keep ? keep[b] : T;
+  const int t0 = blockIdx.x * rows_per_cta;
+  for (int t = t0; t < t0 + rows_per_cta && t < T; ++t) {
+    float* q = feats + ((size_t)b * T + t) * F + m;
+    *q = (t < kp) ? (*q - mean) : 0.f;
+  }
+}
+
+size_t frontend_smem_bytes(int N, int WL, int hop, int fpb) {
+  const int G = (N / 4 < 256) ? N / 4 : 256;
+  const int NG = 256 / G;
+  const int span = (fpb - 1) * hop + WL;
+  size_t fl = ((span + 3) & ~3) + ((WL + 3) & ~3) + 2 * (size_t)N + 2 * 2 * (size_t)NG * N + 2 * NG + 4;
+  return fl * sizeof(float);
+}
+
+cudaError_t launch_frontend(const FrontendParams& p, const int* keep, cudaStream_t stream) {
+  size_t smem = frontend_smem_bytes(p.N, p.WL, p.hop, p.fpb);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  dim3 grid(p.nblk, p.B);
+  frontend_kernel<<<grid, 256, smem, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int rows = 64;
+  dim3 g2((p.T + rows - 1) / rows, p.B);
+  cmn_mask_kernel<<<g2, 128, 0, stream>>>(p.feats, p.partial, keep, p.T, p.F, p.nblk, rows);
+  return cudaGetLastError();
+}
+
+}  // namespace vpb

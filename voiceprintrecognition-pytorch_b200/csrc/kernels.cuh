@@ -1,0 +1,44 @@
+// Kernel parameter blocks + host launchers shared between translation units.
+#pragma once
+#include "common.cuh"
+
+namespace vpb {
+
+struct FrontendParams {
+  const float* wave; float* feats; float* partial;
+  const float* window; const float2* twiddle;
+  const int* mel_start; const int* mel_count; const int* mel_off; const float* mel_w;
+  int B, L, T, kind, N, WL, hop, F, remove_dc, power, use_log, fpb, nblk;
+  float preemph, log_floor;
+};
+
+struct StatsParams {
+  const float* src; float* dst;
+  int B, R, C, in_ld, in_coff, out_ld, out_coff, mode, seg_len, n_seg;
+  float eps;
+};
+
+// x: [B,T,C] view (x_ld/x_coff), logits likewise; dst[b, c] = mean, dst[b, C + c] = std.
+struct AspParams {
+  const float* x; const float* logit; float* dst;
+  int B, T, C, x_ld, x_coff, l_ld, l_coff, out_ld, out_coff;
+  float eps;
+};
+
+struct EwParams {
+  const float* x; const float* y; const float* att; const float* gate; const float* res; float* dst;
+  long long rows; int C, rows_per_utt;
+  int x_ld, x_coff, y_ld, y_coff, att_ld, att_coff, res_ld, res_coff, out_ld, out_coff, mode, act2;
+};
+
+cudaError_t launch_frontend(const FrontendParams& p, const int* keep, cudaStream_t stream);
+cudaError_t launch_conv_ffma(const ConvParams& p, cudaStream_t stream);
+cudaError_t launch_conv_c1(const ConvParams& p, cudaStream_t stream);
+cudaError_t launch_colstats(const StatsParams& p, cudaStream_t stream);
+cudaError_t launch_asp_pool(const AspParams& p, cudaStream_t stream);
+cudaError_t launch_ew(const EwParams& p, cudaStream_t stream);
+// tcgen05 engine (conv_tc.cu)
+bool conv_tc_supported(const ConvParams& p);
+cudaError_t launch_conv_tc(const ConvParams& p, cudaStream_t stream);
+
+}  // namespace vpb

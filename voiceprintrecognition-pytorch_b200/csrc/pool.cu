@@ -1,0 +1,185 @@
+// Whole-utterance reductions and elementwise glue of the backbones (all channel-last, lane <-> channel so every
+// warp-level load is a coalesced 128 B row segment):
+//   colstats   : SE squeeze (ecapa_tdnn.py:79, resnet_se.py:58-60), ASP global mean/std (pooling.py:91-94,108),
+//                CAM++ StatsPool (campplus.py:27-33), TSTP (pooling.py:140-148), CAM++ context (campplus.py:96-111)
+//   asp_pool   : softmax over time + attentive mean/std (pooling.py:120-126)
+//   ew         : SE excite + residual (ecapa_tdnn.py:84,143; resnet_se.py:40-44), AFF blend (eres2net.py:48-50)
+#include "kernels.cuh"
+
+namespace vpb {
+
+// grid (ceil(C/32), B), block 256 = 8 warps; lane = channel, warps stride over the R rows.
+__global__ void __launch_bounds__(256) colstats_kernel(const __grid_constant__ StatsParams p) {
+  __shared__ float red[8][33];
+  __shared__ float bc[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int b = blockIdx.y;
+  const bool ok = c < p.C;
+  const float* x = p.src + (size_t)b * p.R * p.in_ld + p.in_coff + c;
+
+  auto block_sum = [&](float v) -> float {      // returns the per-channel total to every warp's lane
+    red[wid][lane] = v;
+    __syncthreads();
+    if (wid == 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += red[i][lane];
+      bc[lane] = s;
+    }
+    __syncthreads();
+    return bc[lane];
+  };
+
+  if (p.mode == VP_STATS_SEG_CONTEXT) {
+    // context[b, s, c] = mean_T(x) + mean over segment s (last segment divides by its in-bounds length)
+    __shared__ float segsum[64][32];
+    float total = 0.f;
+    for (int s = 0; s < p.n_seg; ++s) {
+      const int r0 = s * p.seg_len, r1 = min(r0 + p.seg_len, p.R);
+      float v = 0.f;
+      if (ok) for (int r = r0 + wid; r < r1; r += 8) v += x[(size_t)r * p.in_ld];
+      const float ss = block_sum(v);
+      if (wid == 0) segsum[s][lane] = ss;
+      total += ss;
+      __syncthreads();
+    }
+    if (wid == 0 && ok) {
+      const float mean = total / (float)p.R;
+      for (int s = 0; s < p.n_seg; ++s) {
+        const int cnt = min(p.seg_len, p.R - s * p.seg_len);
+        p.dst[((size_t)b * p.n_seg + s) * p.out_ld + p.out_coff + c] = mean + segsum[s][lane] / (float)cnt;
+      }
+    }
+    return;
+  }
+
+  float v = 0.f;
+  if (ok) for (int r = wid; r < p.R; r += 8) v += x[(size_t)r * p.in_ld];
+  const float mean = block_sum(v) / (float)p.R;
+  float* o = p.dst + (size_t)b * p.out_ld + p.out_coff;
+  if (p.mode == VP_STATS_MEAN) {
+    if (wid == 0 && ok) o[c] = mean;
+    return;
+  }
+  __syncthreads();
+  float q = 0.f;
+  if (ok) for (int r = wid; r < p.R; r += 8) { float d = x[(size_t)r * p.in_ld] - mean; q = fmaf(d, d, q); }
+  const float ssq = block_sum(q);
+  if (wid == 0 && ok) {
+    float sd;
+    if (p.mode == VP_STATS_MEAN_STD_CLAMP) sd = sqrtf(fmaxf(ssq / (float)p.R, p.eps));
+    else if (p.mode == VP_STATS_MEAN_STD_UNBIASED) sd = sqrtf(ssq / (float)(p.R - 1));
+    else sd = sqrtf(ssq / (float)(p.R - 1) + p.eps);
+    o[c] = mean;
+    o[p.C + c] = sd;
+  }
+}
+
+cudaError_t launch_colstats(const StatsParams& p, cudaStream_t stream) {
+  dim3 grid((p.C + 31) / 32, p.B);
+  colstats_kernel<<<grid, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// Attentive statistics: alpha = softmax_t(logit[b, t, c]); mean = sum alpha x; std = sqrt(clamp(sum alpha (x-mean)^2, eps)).
+// x: src (in_ld/in_coff), logits: src2 (l_ld/l_coff); dst[b, c] = mean, dst[b, C + c] = std.
+__global__ void __launch_bounds__(256) asp_pool_kernel(const __grid_constant__ AspParams p) {
+  __shared__ float red[8][33];
+  __shared__ float bc[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int b = blockIdx.y;
+  const bool ok = c < p.C;
+  const float* x = p.x + (size_t)b * p.T * p.x_ld + p.x_coff + c;
+  const float* l = p.logit + (size_t)b * p.T * p.l_ld + p.l_coff + c;
+
+  auto block_reduce = [&](float v, bool is_max) -> float {
+    red[wid][lane] = v;
+    __syncthreads();
+    if (wid == 0) {
+      float s = red[0][lane];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) s = is_max ? fmaxf(s, red[i][lane]) : s + red[i][lane];
+      bc[lane] = s;
+    }
+    __syncthreads();
+    float r = bc[lane];
+    __syncthreads();
+    return r;
+  };
+
+  float mx = -INFINITY;
+  if (ok) for (int t = wid; t < p.T; t += 8) mx = fmaxf(mx, l[(size_t)t * p.l_ld]);
+  mx = block_reduce(mx, true);
+  float se = 0.f, sx = 0.f;
+  if (ok) for (int t = wid; t < p.T; t += 8) {
+    const float e = expf(l[(size_t)t * p.l_ld] - mx);
+    se += e;
+    sx = fmaf(e, x[(size_t)t * p.x_ld], sx);
+  }
+  se = block_reduce(se, false);
+  sx = block_reduce(sx, false);
+  const float mean = sx / se;
+  float sq = 0.f;
+  if (ok) for (int t = wid; t < p.T; t += 8) {
+    const float e = expf(l[(size_t)t * p.l_ld] - mx);
+    const float d = x[(size_t)t * p.x_ld] - mean;
+    sq = fmaf(e, d * d, sq);
+  }
+  sq = block_reduce(sq, false);
+  if (wid == 0 && ok) {
+    float* o = p.dst + (size_t)b * p.out_ld + p.out_coff;
+    o[c] = mean;
+    o[p.C + c] = sqrtf(fmaxf(sq / se, p.eps));
+  }
+}
+
+cudaError_t launch_asp_pool(const AspParams& p, cudaStream_t stream) {
+  dim3 grid((p.C + 31) / 32, p.B);
+  asp_pool_kernel<<<grid, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// Elementwise ops over [rows, C] (C % 4 == 0), float4 vectorised.
+__global__ void __launch_bounds__(256) ew_kernel(const __grid_constant__ EwParams p) {
+  const int c4n = p.C >> 2;
+  const long long total = p.rows * c4n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / c4n;
+    const int c = (int)(i - m * c4n) * 4;
+    float4 v = *reinterpret_cast<const float4*>(p.x + m * p.x_ld + p.x_coff + c);
+    if (p.mode == VP_EW_GATE_RES) {
+      if (p.gate) {
+        const long long b = m / p.rows_per_utt;
+        const float4 g = *reinterpret_cast<const float4*>(p.gate + b * p.C + c);
+        v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+      }
+      if (p.res) {
+        const float4 r = *reinterpret_cast<const float4*>(p.res + m * p.res_ld + p.res_coff + c);
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      }
+      v.x = apply_act(v.x, p.act2); v.y = apply_act(v.y, p.act2); v.z = apply_act(v.z, p.act2); v.w = apply_act(v.w, p.act2);
+    } else if (p.mode == VP_EW_AFF) {
+      const float4 y = *reinterpret_cast<const float4*>(p.y + m * p.y_ld + p.y_coff + c);
+      const float4 a = *reinterpret_cast<const float4*>(p.att + m * p.att_ld + p.att_coff + c);
+      float ax = 1.f + tanhf(a.x), ay = 1.f + tanhf(a.y), az = 1.f + tanhf(a.z), aw = 1.f + tanhf(a.w);
+      v.x = v.x * ax + y.x * (2.f - ax);
+      v.y = v.y * ay + y.y * (2.f - ay);
+      v.z = v.z * az + y.z * (2.f - az);
+      v.w = v.w * aw + y.w * (2.f - aw);
+    }
+    *reinterpret_cast<float4*>(p.dst + m * p.out_ld + p.out_coff + c) = v;
+  }
+}
+
+cudaError_t launch_ew(const EwParams& p, cudaStream_t stream) {
+  long long total = p.rows * (p.C >> 2);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (blocks < 1) blocks = 1;
+  ew_kernel<<<(int)blocks, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace vpb

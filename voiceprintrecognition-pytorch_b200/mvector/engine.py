@@ -1,0 +1,324 @@
+"""Host-side runtime over the C ABI: device handle, packed weight arena, static memory planner and the program
+builder the model mirrors (mvector/models/*.py) lower themselves with.
+
+torch is used for device memory, streams and (multi-GPU) torch.distributed only; every kernel on the path is in
+libvpb200.so.
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+ALIGN = 256  # bytes; every workspace buffer / weight tensor starts on a 256 B boundary
+
+
+def _check(handle, rc):
+    if rc != L.VP_OK:
+        msg = L.lib().vp_last_error(handle).decode('utf-8', 'replace') if handle else ''
+        raise L.VpError(rc, msg)
+
+
+class Engine:
+    """One per (process, device): owns the vp_handle, the weight arena and the front-end state."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('CUDA device required: the vpb200 path has no CPU fallback')
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        self._h = C.c_void_p()
+        rc = L.lib().vp_create(self.device.index, C.byref(self._h))
+        if rc != L.VP_OK:
+            raise L.VpError(rc, 'vp_create failed (needs an sm_100 GPU)')
+        self._programs = []
+
+    @property
+    def handle(self):
+        return self._h
+
+    def stream_ptr(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def load_weights(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.float32)
+        _check(self._h, L.lib().vp_weights_load(self._h, blob.ctypes.data_as(C.c_void_p), blob.nbytes))
+
+    def close(self):
+        if self._h:
+            for p in self._programs:
+                p.close()
+            L.lib().vp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class WeightArena:
+    """Packs fp32 tensors into one blob; returns byte offsets (256 B aligned)."""
+
+    def __init__(self):
+        self._chunks = []
+        self._size = 0
+        self.index = OrderedDict()
+
+    def add(self, name, arr):
+        a = np.ascontiguousarray(np.asarray(arr, dtype=np.float32)).reshape(-1)
+        off = self._size
+        pad = (-a.nbytes) % ALIGN
+        self._chunks.append(a)
+        if pad:
+            self._chunks.append(np.zeros(pad // 4, dtype=np.float32))
+        self._size += a.nbytes + pad
+        self.index[name] = (off, a.size)
+        return off
+
+    def blob(self):
+        return np.concatenate(self._chunks) if self._chunks else np.zeros(64, dtype=np.float32)
+
+
+class View:
+    """A [rows, C] window into an activation buffer: byte offset, row stride (floats), first column, columns."""
+    __slots__ = ('off', 'ld', 'coff', 'C')
+
+    def __init__(self, off, ld, coff, C_):
+        self.off, self.ld, self.coff, self.C = off, ld, coff, C_
+
+    def cols(self, start, n):
+        assert 0 <= start and start + n <= self.C
+        return View(self.off, self.ld, self.coff + start, n)
+
+
+INPUT = 'input'
+OUTPUT = 'output'
+
+
+class PlanBuilder:
+    """Accumulates vp_ops and plans the workspace (first-fit free list: buffers are freed explicitly by the model
+    lowering code once their last consumer has been emitted, so big 2-D maps are reused)."""
+
+    def __init__(self, B, engine_pref=L.ENGINE_AUTO):
+        self.B = B
+        self.ops = []
+        self.engine_pref = engine_pref
+        self._free = []          # sorted list of [start, end)
+        self._top = 0
+        self._live = {}
+        self.peak = 0
+        self.in_floats = 0
+        self.out_floats = 0
+        self.taps = OrderedDict()   # name -> (View, rows) for tests (vp_program_peek)
+
+    # ---- memory ----
+    def alloc(self, rows, cols):
+        nbytes = (rows * cols * 4 + ALIGN - 1) // ALIGN * ALIGN
+        for i, (s, e) in enumerate(self._free):
+            if e - s >= nbytes:
+                if e - s == nbytes:
+                    self._free.pop(i)
+                else:
+                    self._free[i][0] = s + nbytes
+                self._live[s] = nbytes
+                return View(s, cols, 0, cols)
+        s = self._top
+        self._top += nbytes
+        self.peak = max(self.peak, self._top)
+        self._live[s] = nbytes
+        return View(s, cols, 0, cols)
+
+    def free(self, view):
+        s = view.off
+        nbytes = self._live.pop(s)
+        self._free.append([s, s + nbytes])
+        self._free.sort()
+        merged = []
+        for iv in self._free:
+            if merged and merged[-1][1] == iv[0]:
+                merged[-1][1] = iv[1]
+            else:
+                merged.append(iv)
+        if merged and merged[-1][1] == self._top:      # give the tail back
+            self._top = merged[-1][0]
+            merged.pop()
+        self._free = merged
+
+    def input_view(self, cols, rows):
+        self.in_floats = rows * cols
+        return View(L.BUF_INPUT, cols, 0, cols)
+
+    def output_view(self, cols, rows):
+        self.out_floats = rows * cols
+        return View(L.BUF_OUTPUT, cols, 0, cols)
+
+    def tap(self, name, view, rows):
+        self.taps[name] = (view, rows)
+
+    # ---- op emitters ----
+    def _new(self, kind):
+        o = L.Op()
+        o.kind = kind
+        o.B = self.B
+        for f in ('src', 'src2', 'dst', 'res', 'gate', 'ubias', 'w', 'bias', 'pre_s', 'pre_h', 'post_s', 'post_h'):
+            setattr(o, f, -1)
+        o.Fin = o.Fout = 1
+        o.KT = o.KF = o.sT = o.sF = o.dT = o.dF = 1
+        o.seg_len, o.n_seg = 1 << 30, 1
+        return o
+
+    def conv(self, src, dst, w, w_ld, Tin, Tout, Fin=1, Fout=1, KT=1, KF=1, sT=1, sF=1, dT=1, dF=1, padT=0, padF=0,
+             pad_mode=L.PAD_ZERO, bias=-1, pre=None, pre_relu=False, post=None, act=L.ACT_NONE, act2=L.ACT_NONE,
+             res=None, gate=None, ubias=None, seg_len=None, n_seg=1, src2=None, src2_mode=L.SRC2_NONE,
+             engine=None, B=None, c1=False):
+        o = self._new(L.OP_CONV_C1 if c1 else L.OP_CONV)
+        if B is not None:
+            o.B = B
+        o.engine = self.engine_pref if engine is None else engine
+        o.src, o.in_ld, o.in_coff, o.Cin = src.off, src.ld, src.coff, src.C
+        o.dst, o.out_ld, o.out_coff, o.Cout = dst.off, dst.ld, dst.coff, dst.C
+        o.Tin, o.Fin, o.Tout, o.Fout = Tin, Fin, Tout, Fout
+        o.KT, o.KF, o.sT, o.sF, o.dT, o.dF, o.padT, o.padF, o.pad_mode = KT, KF, sT, sF, dT, dF, padT, padF, pad_mode
+        o.w, o.w_ld, o.bias = w, w_ld, bias
+        if pre is not None:
+            o.pre_s, o.pre_h = pre
+            o.pre_relu = 1 if pre_relu else 0
+        if post is not None:
+            o.post_s, o.post_h = post
+        o.act, o.act2 = act, act2
+        if res is not None:
+            assert res.C == dst.C
+            o.res, o.res_ld, o.res_coff = res.off, res.ld, res.coff
+        if gate is not None:
+            o.gate = gate.off
+        if ubias is not None:
+            o.ubias = ubias.off
+        if seg_len is not None:
+            o.seg_len, o.n_seg = seg_len, n_seg
+        if src2 is not None:
+            o.src2, o.src2_ld, o.src2_coff, o.src2_mode = src2.off, src2.ld, src2.coff, src2_mode
+            if src2_mode == L.SRC2_CONCAT:
+                o.Cin2 = src2.C
+            else:
+                assert src2.C == src.C
+        self._check_conv(o)
+        self.ops.append(o)
+        return o
+
+    @staticmethod
+    def _check_conv(o):
+        """Same alignment rules the C validator enforces (api.cu validate_op), raised early on the host."""
+        def a4(*vals):
+            return all(v % 4 == 0 for v in vals)
+        if o.kind == L.OP_CONV_C1:
+            ok = o.Cin == 1 and a4(o.Cout, o.out_ld, o.out_coff)
+        else:
+            ok = a4(o.Cin, o.in_ld, o.in_coff, o.w_ld, o.Cin2)
+            if o.src2_mode != L.SRC2_NONE:
+                ok = ok and a4(o.src2_ld, o.src2_coff)
+        if not ok:
+            raise ValueError('conv op: channel counts / strides / offsets must be multiples of 4 floats '
+                             f'(Cin={o.Cin}, Cin2={o.Cin2}, in_ld={o.in_ld}, in_coff={o.in_coff}, w_ld={o.w_ld})')
+
+    def colstats(self, src, dst, rows_per_utt, mode, eps=0.0, seg_len=None, n_seg=1):
+        o = self._new(L.OP_COLSTATS)
+        o.mode = mode
+        o.src, o.in_ld, o.in_coff, o.Cin = src.off, src.ld, src.coff, src.C
+        o.dst, o.out_ld, o.out_coff = dst.off, dst.ld, dst.coff
+        o.Tin, o.Fin = rows_per_utt, 1
+        o.eps = eps
+        if seg_len is not None:
+            o.seg_len, o.n_seg = seg_len, n_seg
+        self.ops.append(o)
+        return o
+
+    def asp_pool(self, x, logits, dst, T, eps=1e-12):
+        o = self._new(L.OP_ASP_POOL)
+        o.src, o.in_ld, o.in_coff, o.Cin = x.off, x.ld, x.coff, x.C
+        o.src2, o.src2_ld, o.src2_coff = logits.off, logits.ld, logits.coff
+        o.dst, o.out_ld, o.out_coff = dst.off, dst.ld, dst.coff
+        o.Tin = T
+        o.eps = eps
+        self.ops.append(o)
+        return o
+
+    def ew(self, mode, x, dst, rows_per_utt, gate=None, res=None, y=None, att=None, act2=L.ACT_NONE):
+        o = self._new(L.OP_EW)
+        o.mode = mode
+        o.src, o.in_ld, o.in_coff, o.Cin = x.off, x.ld, x.coff, x.C
+        o.dst, o.out_ld, o.out_coff = dst.off, dst.ld, dst.coff
+        o.Tin, o.Fin = rows_per_utt, 1
+        o.act2 = act2
+        if gate is not None:
+            o.gate = gate.off
+        if res is not None:
+            o.res, o.res_ld, o.res_coff = res.off, res.ld, res.coff
+        if y is not None:
+            o.src2, o.src2_ld, o.src2_coff = y.off, y.ld, y.coff
+        if att is not None:
+            o.res, o.res_ld, o.res_coff = att.off, att.ld, att.coff
+        self.ops.append(o)
+        return o
+
+
+class Program:
+    """A compiled (validated, workspace-backed) program for one (B, T)."""
+
+    def __init__(self, engine, pb):
+        self.engine = engine
+        self.n_ops = len(pb.ops)
+        self.ws_bytes = max(pb.peak, ALIGN)
+        self.in_floats, self.out_floats = pb.in_floats, pb.out_floats
+        self.taps = pb.taps
+        arr = (L.Op * self.n_ops)(*pb.ops)
+        self._p = C.c_void_p()
+        _check(engine.handle, L.lib().vp_program_create(engine.handle, arr, self.n_ops, self.ws_bytes,
+                                                        self.in_floats, self.out_floats, C.byref(self._p)))
+        engine._programs.append(self)
+
+    @property
+    def launches(self):
+        return int(L.lib().vp_program_launches(self._p))
+
+    def run(self, feats, emb):
+        assert feats.is_cuda and feats.dtype == torch.float32 and feats.is_contiguous()
+        assert emb.is_cuda and emb.dtype == torch.float32 and emb.is_contiguous()
+        assert feats.numel() == self.in_floats and emb.numel() == self.out_floats
+        _check(self.engine.handle, L.lib().vp_embed(self._p, C.c_void_p(feats.data_ptr()), C.c_void_p(emb.data_ptr()),
+                                                    self.engine.stream_ptr()))
+
+    def run_wave(self, wave, keep, feats_scratch, fe_scratch, emb):
+        B, Lpad = wave.shape
+        kp = C.c_void_p(keep.data_ptr()) if keep is not None else C.c_void_p()
+        _check(self.engine.handle, L.lib().vp_embed_wave(
+            self._p, C.c_void_p(wave.data_ptr()), B, Lpad, kp, C.c_void_p(feats_scratch.data_ptr()),
+            C.c_void_p(fe_scratch.data_ptr()), C.c_void_p(emb.data_ptr()), self.engine.stream_ptr()))
+
+    def peek(self, name):
+        """Copy a tapped intermediate out of the workspace (tests only)."""
+        view, rows = self.taps[name]
+        n = (rows - 1) * view.ld + view.coff + view.C
+        buf = torch.empty(n, dtype=torch.float32, device=self.engine.device)
+        _check(self.engine.handle, L.lib().vp_program_peek(self._p, view.off, n * 4, C.c_void_p(buf.data_ptr()),
+                                                           self.engine.stream_ptr()))
+        full = torch.zeros(rows * view.ld, dtype=torch.float32, device=self.engine.device)
+        full[:n] = buf
+        return full.view(rows, view.ld)[:, view.coff:view.coff + view.C]
+
+    def close(self):
+        if self._p:
+            L.lib().vp_program_destroy(self._p)
+            self._p = C.c_void_p()
+
+
+_ENGINES = {}
+
+
+def get_engine(device=None):
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    if idx not in _ENGINES:
+        _ENGINES[idx] = Engine(idx)
+    return _ENGINES[idx]

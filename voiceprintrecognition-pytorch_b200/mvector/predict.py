@@ -1,0 +1,273 @@
+"""MVectorPredictor: drop-in for mvector.predict.MVectorPredictor (reference: mvector/predict.py:22-395) on the
+B200-native path.  Constructor and method signatures, argument meaning and error behaviour follow the reference;
+``predict`` / ``predict_batch`` / ``contrast`` run entirely on hand-written sm_100a kernels through libvpb200.so.
+
+Differences that are deliberate:
+  * ``use_gpu=False`` raises: this path has no CPU implementation (the reference's CPU path is the oracle).
+  * ``predict_batch`` feeds the WHOLE padded batch to the device in one ``vp_embed_wave`` call (front-end + backbone);
+    the reference's ``batch_size`` argument (predict.py:261) is accepted and ignored -- chunking does not change
+    results because every op is per-utterance, and padding/CMN/mask are computed on the full batch exactly like
+    predict.py:244-258.
+  * ``speaker_diarization`` (predict.py:365-395: VAD + spectral clustering on CPU) is outside the hot path and raises
+    NotImplementedError.
+"""
+import os
+import pickle
+import shutil
+from io import BufferedReader
+
+import numpy as np
+import torch
+import yaml
+from loguru import logger
+
+from .audio import AudioSegment
+from .data_utils.featurizer import AudioFeaturizer
+from .engine import Engine
+from .models import build_model
+from .utils.checkpoint import load_pretrained
+from .utils.utils import dict_to_object, print_arguments
+
+
+class MVectorPredictor:
+    def __init__(self, configs, threshold=0.6, audio_db_path=None, model_path='models/CAMPPlus_Fbank/best_model/',
+                 use_gpu=True):
+        if use_gpu:
+            assert torch.cuda.is_available(), 'GPU不可用'
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        else:
+            raise RuntimeError('use_gpu=False: the B200-native path has no CPU implementation')
+        self.threshold = threshold
+        if isinstance(configs, str):
+            with open(configs, 'r', encoding='utf-8') as f:
+                configs = yaml.load(f.read(), Loader=yaml.FullLoader)
+            print_arguments(configs=configs)
+        self.configs = dict_to_object(configs)
+        self._engine = Engine(self.device.index)
+        self._audio_featurizer = AudioFeaturizer(feature_method=self.configs.preprocess_conf.feature_method,
+                                                 use_hf_model=self.configs.preprocess_conf.get('use_hf_model', False),
+                                                 method_args=self.configs.preprocess_conf.get('method_args', {}),
+                                                 engine=self._engine)
+        self.predictor = build_model(input_size=self._audio_featurizer.feature_dim, configs=self.configs)
+        self.predictor.engine = self._engine
+        if os.path.isdir(model_path):
+            model_path = os.path.join(model_path, 'model.pth')
+        assert os.path.exists(model_path), f"{model_path} 模型不存在！"
+        self.predictor = load_pretrained(self.predictor, model_path, use_gpu=use_gpu)
+        logger.info(f"成功加载模型参数：{model_path}")
+        self.predictor.eval()
+        self._pinned = None
+
+        self.audio_feature = None
+        self.audio_feature_mean = None
+        self.users_name = []
+        self.users_audio_path = []
+        self.users_name_mean = []
+        self.audio_db_path = audio_db_path
+        if self.audio_db_path is not None:
+            self.audio_indexes_path = os.path.join(audio_db_path, "audio_indexes.bin")
+            self.__load_audio_db(self.audio_db_path)
+
+    # ------------------------------------------------------------------ voiceprint DB (numpy glue, predict.py:85-183)
+    def __load_audio_indexes(self):
+        if not os.path.exists(self.audio_indexes_path):
+            return
+        with open(self.audio_indexes_path, "rb") as f:
+            indexes = pickle.load(f)
+        for name, feature, path in zip(indexes["users_name"], indexes["faces_feature"], indexes["users_image_path"]):
+            if not os.path.exists(path):
+                continue
+            self.users_name.append(name)
+            self.users_audio_path.append(path)
+            self.audio_feature = feature if self.audio_feature is None else np.vstack((self.audio_feature, feature))
+
+    def __write_index(self):
+        with open(self.audio_indexes_path, "wb") as f:
+            pickle.dump({"users_name": self.users_name, "faces_feature": self.audio_feature,
+                         "users_image_path": self.users_audio_path}, f)
+
+    def __refresh_means(self):
+        self.audio_feature_mean, self.users_name_mean = None, []
+        for name in set(self.users_name):
+            idx = [i for i, v in enumerate(self.users_name) if v == name]
+            feature = self.audio_feature[idx].mean(axis=0)
+            self.audio_feature_mean = feature if self.audio_feature_mean is None \
+                else np.vstack((self.audio_feature_mean, feature))
+            self.users_name_mean.append(name)
+        if self.audio_feature_mean is not None and len(self.audio_feature_mean.shape) == 1:
+            self.audio_feature_mean = self.audio_feature_mean[np.newaxis, :]
+
+    def __load_audio_db(self, audio_db_path):
+        self.__load_audio_indexes()
+        os.makedirs(audio_db_path, exist_ok=True)
+        paths = []
+        for name in os.listdir(audio_db_path):
+            d = os.path.join(audio_db_path, name)
+            if not os.path.isdir(d):
+                continue
+            for file in os.listdir(d):
+                paths.append(os.path.join(d, file).replace('\\', '/'))
+        if len(paths) == 0:
+            return
+        logger.info('正在加载声纹库数据...')
+        bs = self.configs.dataset_conf.eval_conf.batch_size
+        pending = []
+        for p in paths:
+            if p in self.users_audio_path:
+                continue
+            seg = self._load_audio(p)
+            self.users_name.append(os.path.basename(os.path.dirname(p)))
+            self.users_audio_path.append(p)
+            pending.append(seg.samples)
+            if len(pending) == bs:
+                feats = self.predict_batch(pending)
+                self.audio_feature = feats if self.audio_feature is None else np.vstack((self.audio_feature, feats))
+                pending = []
+        if pending:
+            feats = self.predict_batch(pending)
+            self.audio_feature = feats if self.audio_feature is None else np.vstack((self.audio_feature, feats))
+        assert len(self.audio_feature) == len(self.users_name) == len(self.users_audio_path), '加载的数量对不上！'
+        self.__write_index()
+        self.__refresh_means()
+        logger.info(f'声纹库数据加载完成，一共有{len(self.audio_feature_mean)}个用户，分别是：{self.users_name_mean}')
+
+    @staticmethod
+    def normalize_features(features):
+        return features / np.linalg.norm(features, axis=1, keepdims=True)
+
+    def __retrieval(self, np_feature):
+        if isinstance(np_feature, list):
+            np_feature = np.array(np_feature)
+        q = self.normalize_features(np_feature.astype(np.float32))
+        db = self.audio_feature_mean / np.linalg.norm(self.audio_feature_mean, axis=1, keepdims=True)
+        labels = []
+        for sim in q @ db.T:                                   # cosine similarity (predict.py:169-183)
+            idx = int(np.argmax(sim))
+            s = sim[idx]
+            labels.append([self.users_name_mean[idx], round(float(s), 5)] if s >= self.threshold else [None, None])
+        return labels
+
+    # ------------------------------------------------------------------ hot path
+    def _load_audio(self, audio_data, sample_rate=16000):
+        """predict.py:185-212: type dispatch, min-duration assert, resample, dB normalisation."""
+        if isinstance(audio_data, str):
+            audio_segment = AudioSegment.from_file(audio_data)
+        elif isinstance(audio_data, BufferedReader):
+            audio_segment = AudioSegment.from_file(audio_data)
+        elif isinstance(audio_data, np.ndarray):
+            audio_segment = AudioSegment.from_ndarray(audio_data, sample_rate)
+        elif isinstance(audio_data, bytes):
+            audio_segment = AudioSegment.from_bytes(audio_data)
+        elif isinstance(audio_data, AudioSegment):
+            audio_segment = audio_data
+        else:
+            raise Exception(f'不支持该数据类型，当前数据类型为：{type(audio_data)}')
+        ds = self.configs.dataset_conf.dataset
+        assert audio_segment.duration >= ds.min_duration, \
+            f'音频太短，最小应该为{ds.min_duration}s，当前音频为{audio_segment.duration}s'
+        if audio_segment.sample_rate != ds.sample_rate:
+            audio_segment.resample(ds.sample_rate)
+        if ds.use_dB_normalization:
+            audio_segment.normalize(target_db=ds.target_dB)
+        return audio_segment
+
+    def _embed_padded(self, inputs, lens_ratio):
+        """inputs: np.float32 [B, Lmax] zero padded -> np.float32 [B, embd_dim].  One H2D, one fused C-ABI call
+        (front-end + backbone), one D2H."""
+        B, Lp = inputs.shape
+        if self._pinned is None or self._pinned.numel() < inputs.size:
+            self._pinned = torch.empty(max(inputs.size, 1 << 20), dtype=torch.float32).pin_memory()
+        host = self._pinned[:inputs.size].view(B, Lp)
+        host.copy_(torch.from_numpy(inputs))
+        wave = host.to(self.device, non_blocking=True)
+        fz = self._audio_featurizer
+        T = fz.num_frames(Lp)
+        if fz.feat_fun.desc.kind == 0:
+            assert 2 <= fz.feat_fun.win_length <= Lp, f'choose a window size {fz.feat_fun.win_length} that is [2, {Lp}]'
+        keep = None
+        if lens_ratio is not None:
+            keep = fz.keep_frames(lens_ratio, T).to(self.device, non_blocking=True)
+        prog = self.predictor.program(B, T)
+        eng = fz.engine
+        from . import _lib as L
+        feats = torch.empty(B * T * fz.feat_fun.n_mels, dtype=torch.float32, device=self.device)
+        scratch = torch.empty(max(int(L.lib().vp_frontend_scratch_floats(eng.handle, B, Lp)), 1), dtype=torch.float32,
+                              device=self.device)
+        emb = torch.empty(B, self.predictor.embd_dim, dtype=torch.float32, device=self.device)
+        prog.run_wave(wave, keep, feats, scratch, emb)
+        return emb.cpu().numpy()
+
+    def predict(self, audio_data, sample_rate=16000):
+        """预测一个音频的特征 (predict.py:214-229) -> np.ndarray [embd_dim]"""
+        seg = self._load_audio(audio_data=audio_data, sample_rate=sample_rate)
+        x = np.ascontiguousarray(seg.samples, dtype=np.float32)[None, :]
+        return self._embed_padded(x, None)[0]
+
+    def predict_batch(self, audios_data, sample_rate=16000, batch_size=32):
+        """预测一批音频的特征 (predict.py:231-265) -> np.ndarray [B, embd_dim], order preserved."""
+        waves = [self._load_audio(audio_data=a, sample_rate=sample_rate).samples for a in audios_data]
+        lmax = max(w.shape[0] for w in waves)
+        inputs = np.zeros((len(waves), lmax), dtype=np.float32)
+        ratio = []
+        for i, w in enumerate(waves):
+            inputs[i, :w.shape[0]] = w
+            ratio.append(w.shape[0] / lmax)
+        return self._embed_padded(inputs, torch.tensor(ratio, dtype=torch.float32))
+
+    def contrast(self, audio_data1, audio_data2):
+        """声纹对比 (predict.py:267-279) -> cosine similarity"""
+        f1 = self.predict(audio_data1)
+        f2 = self.predict(audio_data2)
+        return np.dot(f1, f2) / (np.linalg.norm(f1) * np.linalg.norm(f2))
+
+    def register(self, audio_data, user_name: str, sample_rate=16000):
+        """声纹注册 (predict.py:281-309)"""
+        seg = self._load_audio(audio_data=audio_data, sample_rate=sample_rate)
+        feature = self.predict(audio_data=seg.samples, sample_rate=seg.sample_rate)
+        if self.audio_feature is None:
+            self.audio_feature = feature
+        else:
+            self.audio_feature = np.vstack((self.audio_feature, feature))
+        if self.audio_feature.ndim == 1:
+            self.audio_feature = self.audio_feature[np.newaxis, :]
+        d = os.path.join(self.audio_db_path, user_name)
+        os.makedirs(d, exist_ok=True)
+        n = len(os.listdir(d))
+        path = os.path.join(d, f'{n}.wav').replace('\\', '/')
+        import wave as _wave
+        with _wave.open(path, 'wb') as w:
+            w.setnchannels(1); w.setsampwidth(2); w.setframerate(seg.sample_rate)
+            w.writeframes((np.clip(seg.samples, -1, 1) * 32767).astype('<i2').tobytes())
+        self.users_audio_path.append(path)
+        self.users_name.append(user_name)
+        self.__write_index()
+        self.__refresh_means()
+        return True, "注册成功"
+
+    def recognition(self, audio_data, threshold=None, sample_rate=16000):
+        """声纹识别 (predict.py:311-333) -> [name-or-None, score-or-None]"""
+        if threshold:
+            self.threshold = threshold
+        feature = self.predict(audio_data, sample_rate=sample_rate)
+        return self.__retrieval(np_feature=[feature])[0]
+
+    def get_users(self):
+        return self.users_name
+
+    def remove_user(self, user_name):
+        """predict.py:343-363"""
+        if user_name not in self.users_name:
+            return False
+        idx = [i for i, n in enumerate(self.users_name) if n == user_name]
+        for i in sorted(idx, reverse=True):
+            self.users_name.pop(i)
+            self.users_audio_path.pop(i)
+        self.audio_feature = np.delete(self.audio_feature, idx, axis=0)
+        self.__write_index()
+        shutil.rmtree(os.path.join(self.audio_db_path, user_name), ignore_errors=True)
+        self.__refresh_means()
+        return True
+
+    def speaker_diarization(self, audio_data, sample_rate=16000, speaker_num=None, search_audio_db=False):
+        raise NotImplementedError('speaker_diarization (predict.py:365-395) is CPU clustering glue outside the '
+                                  'B200 hot path (SURVEY.md 2, row 9); it is a caller of predict_batch')
