@@ -147,6 +147,11 @@ int vp_embed(vp_program* p, const float* feats, float* emb, void* stream);
 /* wave [B,Lpad] -> emb: front-end then program; feats_scratch holds B*T*F floats, fe_scratch as for vp_fbank */
 int vp_embed_wave(vp_program* p, const float* wave, int32_t B, int32_t Lpad, const int32_t* keep_frames,
                   float* feats_scratch, float* fe_scratch, float* emb, void* stream);
+/* Same as vp_embed but brackets every op with CUDA events on `stream`, synchronises, and writes the per-op device
+ * time in milliseconds to the HOST array ms_per_op[n_ops] (bench.py's live roofline measurement). */
+int vp_embed_profiled(vp_program* p, const float* feats, float* emb, void* stream, float* ms_per_op);
+/* op i of the program: kind, GEMM view (M rows, N = Cout, K = taps*Cin; K = 0 for non-conv ops), resolved engine */
+int vp_program_op_info(const vp_program* p, int32_t i, int32_t* kind, int64_t* M, int64_t* N, int64_t* K, int32_t* engine);
 /* number of kernel launches one vp_embed enqueues (bench.py's gpu_launches) */
 int32_t vp_program_launches(const vp_program* p);
 /* debugging / tests: copy a workspace region to a caller device buffer on the stream */

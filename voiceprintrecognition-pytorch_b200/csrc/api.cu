@@ -32,6 +32,7 @@ struct vp_handle {
 struct vp_program {
   vp_handle* h = nullptr;
   std::vector<vp_op> ops;
+  std::vector<int> engines;   // resolved conv engine per op (VP_ENGINE_FFMA / VP_ENGINE_TC), 0 for non-conv
   char* d_ws = nullptr;
   size_t ws_bytes = 0, in_floats = 0, out_floats = 0;
   int launches = 0;
@@ -55,6 +56,8 @@ static int fail(vp_handle* h, int code, const char* fmt, ...) {
 static const int FPB = 16;   // frames per front-end CTA
 
 extern "C" {
+
+static void fill_conv(const vp_program* p, const vp_op& o, const float* feats, float* emb, vpb::ConvParams& c);
 
 int vp_abi_version(void) { return VP_ABI_VERSION; }
 int32_t vp_sizeof_op(void) { return (int32_t)sizeof(vp_op); }
@@ -341,6 +344,20 @@ int vp_program_create(vp_handle* h, const vp_op* ops, int32_t n_ops, size_t ws_b
     if (r != VP_OK) { delete p; return r; }
   }
   p->launches = n_ops;
+  p->engines.assign(n_ops, 0);
+  for (int i = 0; i < n_ops; ++i) {
+    const vp_op& o = p->ops[i];
+    if (o.kind != VP_OP_CONV) continue;
+    ConvParams c;
+    fill_conv(p, o, nullptr, nullptr, c);
+    const bool ok = conv_tc_supported(c);
+    if (o.engine == VP_ENGINE_TC && !ok) {
+      int r = fail(h, VP_ERR_UNSUPPORTED, "op %d: shape not supported by the tcgen05 engine", i);
+      delete p;
+      return r;
+    }
+    p->engines[i] = (o.engine == VP_ENGINE_TC || (o.engine == VP_ENGINE_AUTO && ok)) ? VP_ENGINE_TC : VP_ENGINE_FFMA;
+  }
   if (cudaSetDevice(h->device) != cudaSuccess || cudaMalloc(&p->d_ws, p->ws_bytes ? p->ws_bytes : 256) != cudaSuccess) {
     delete p;
     return fail(h, VP_ERR_NOMEM, "workspace of %zu bytes: %s", ws_bytes, cudaGetErrorString(cudaGetLastError()));
@@ -368,39 +385,39 @@ static inline const float* wt(const vp_program* p, int64_t off) {
   return off < 0 ? nullptr : reinterpret_cast<const float*>(reinterpret_cast<const char*>(p->h->d_weights) + off);
 }
 
-int vp_embed(vp_program* p, const float* feats, float* emb, void* stream) {
-  if (!p || !feats || !emb) return p ? fail(p->h, VP_ERR_INVALID, "null argument") : VP_ERR_INVALID;
+static void fill_conv(const vp_program* p, const vp_op& o, const float* feats, float* emb, ConvParams& c) {
+  c.src = rd(p, o.src, feats, emb);
+  c.src2 = o.src2_mode == VP_SRC2_NONE ? nullptr : rd(p, o.src2, feats, emb);
+  c.dst = const_cast<float*>(rd(p, o.dst, feats, emb));
+  c.res = rd(p, o.res, feats, emb); c.gate = rd(p, o.gate, feats, emb); c.ubias = rd(p, o.ubias, feats, emb);
+  c.w = wt(p, o.w); c.bias = wt(p, o.bias); c.pre_s = wt(p, o.pre_s); c.pre_h = wt(p, o.pre_h);
+  c.post_s = wt(p, o.post_s); c.post_h = wt(p, o.post_h);
+  c.B = o.B; c.Tin = o.Tin; c.Fin = o.Fin; c.Cin = o.Cin;
+  c.CinTot = o.Cin + (o.src2_mode == VP_SRC2_CONCAT ? o.Cin2 : 0);
+  c.in_ld = o.in_ld; c.in_coff = o.in_coff;
+  c.src2_mode = o.src2_mode; c.src2_ld = o.src2_ld; c.src2_coff = o.src2_coff;
+  c.Tout = o.Tout; c.Fout = o.Fout; c.out_ld = o.out_ld; c.out_coff = o.out_coff;
+  c.res_ld = o.res_ld; c.res_coff = o.res_coff;
+  c.KT = o.KT; c.KF = o.KF; c.sT = o.sT; c.sF = o.sF; c.dT = o.dT; c.dF = o.dF; c.padT = o.padT; c.padF = o.padF;
+  c.pad_mode = o.pad_mode; c.w_ld = o.w_ld; c.pre_relu = o.pre_relu; c.act = o.act; c.act2 = o.act2;
+  c.seg_len = o.seg_len; c.n_seg = o.n_seg;
+  c.M = o.B * o.Tout * o.Fout; c.N = o.Cout; c.K = o.KT * o.KF * c.CinTot;
+}
+
+static int run_ops(vp_program* p, const float* feats, float* emb, cudaStream_t st, cudaEvent_t* evs) {
   vp_handle* h = p->h;
-  cudaStream_t st = (cudaStream_t)stream;
   for (size_t i = 0; i < p->ops.size(); ++i) {
     const vp_op& o = p->ops[i];
+    if (evs) CUDA_TRY(h, cudaEventRecord(evs[i], st));
     switch (o.kind) {
       case VP_OP_CONV:
       case VP_OP_CONV_C1: {
         ConvParams c;
-        c.src = rd(p, o.src, feats, emb);
-        c.src2 = o.src2_mode == VP_SRC2_NONE ? nullptr : rd(p, o.src2, feats, emb);
-        c.dst = const_cast<float*>(rd(p, o.dst, feats, emb));
-        c.res = rd(p, o.res, feats, emb); c.gate = rd(p, o.gate, feats, emb); c.ubias = rd(p, o.ubias, feats, emb);
-        c.w = wt(p, o.w); c.bias = wt(p, o.bias); c.pre_s = wt(p, o.pre_s); c.pre_h = wt(p, o.pre_h);
-        c.post_s = wt(p, o.post_s); c.post_h = wt(p, o.post_h);
-        c.B = o.B; c.Tin = o.Tin; c.Fin = o.Fin; c.Cin = o.Cin;
-        c.CinTot = o.Cin + (o.src2_mode == VP_SRC2_CONCAT ? o.Cin2 : 0);
-        c.in_ld = o.in_ld; c.in_coff = o.in_coff;
-        c.src2_mode = o.src2_mode; c.src2_ld = o.src2_ld; c.src2_coff = o.src2_coff;
-        c.Tout = o.Tout; c.Fout = o.Fout; c.out_ld = o.out_ld; c.out_coff = o.out_coff;
-        c.res_ld = o.res_ld; c.res_coff = o.res_coff;
-        c.KT = o.KT; c.KF = o.KF; c.sT = o.sT; c.sF = o.sF; c.dT = o.dT; c.dF = o.dF; c.padT = o.padT; c.padF = o.padF;
-        c.pad_mode = o.pad_mode; c.w_ld = o.w_ld; c.pre_relu = o.pre_relu; c.act = o.act; c.act2 = o.act2;
-        c.seg_len = o.seg_len; c.n_seg = o.n_seg;
-        c.M = o.B * o.Tout * o.Fout; c.N = o.Cout; c.K = o.KT * o.KF * c.CinTot;
+        fill_conv(p, o, feats, emb, c);
         if (o.kind == VP_OP_CONV_C1) {
           CUDA_TRY(h, launch_conv_c1(c, st));
         } else {
-          bool use_tc = o.engine == VP_ENGINE_TC || (o.engine == VP_ENGINE_AUTO && conv_tc_supported(c));
-          if (o.engine == VP_ENGINE_TC && !conv_tc_supported(c))
-            return fail(h, VP_ERR_UNSUPPORTED, "op %zu: shape not supported by the tcgen05 engine", i);
-          if (use_tc) CUDA_TRY(h, launch_conv_tc(c, st));
+          if (p->engines[i] == VP_ENGINE_TC) CUDA_TRY(h, launch_conv_tc(c, st));
           else CUDA_TRY(h, launch_conv_ffma(c, st));
         }
         break;
@@ -441,6 +458,45 @@ int vp_embed(vp_program* p, const float* feats, float* emb, void* stream) {
       default:
         return fail(h, VP_ERR_INVALID, "op %zu: unknown kind", i);
     }
+  }
+  if (evs) CUDA_TRY(h, cudaEventRecord(evs[p->ops.size()], st));
+  return VP_OK;
+}
+
+int vp_embed(vp_program* p, const float* feats, float* emb, void* stream) {
+  if (!p || !feats || !emb) return p ? fail(p->h, VP_ERR_INVALID, "null argument") : VP_ERR_INVALID;
+  return run_ops(p, feats, emb, (cudaStream_t)stream, nullptr);
+}
+
+int vp_embed_profiled(vp_program* p, const float* feats, float* emb, void* stream, float* ms_per_op) {
+  if (!p || !feats || !emb || !ms_per_op) return p ? fail(p->h, VP_ERR_INVALID, "null argument") : VP_ERR_INVALID;
+  vp_handle* h = p->h;
+  const size_t n = p->ops.size();
+  std::vector<cudaEvent_t> evs(n + 1);
+  for (auto& e : evs) CUDA_TRY(h, cudaEventCreate(&e));
+  int r = run_ops(p, feats, emb, (cudaStream_t)stream, evs.data());
+  if (r == VP_OK) {
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) r = fail(h, VP_ERR_CUDA, "sync: %s", cudaGetErrorString(e));
+  }
+  if (r == VP_OK)
+    for (size_t i = 0; i < n; ++i) cudaEventElapsedTime(&ms_per_op[i], evs[i], evs[i + 1]);
+  for (auto& e : evs) cudaEventDestroy(e);
+  return r;
+}
+
+int vp_program_op_info(const vp_program* p, int32_t i, int32_t* kind, int64_t* M, int64_t* N, int64_t* K, int32_t* engine) {
+  if (!p || i < 0 || (size_t)i >= p->ops.size()) return VP_ERR_INVALID;
+  const vp_op& o = p->ops[i];
+  *kind = o.kind;
+  *engine = 0;
+  if (o.kind == VP_OP_CONV || o.kind == VP_OP_CONV_C1) {
+    *M = (int64_t)o.B * o.Tout * o.Fout;
+    *N = o.Cout;
+    *K = (int64_t)o.KT * o.KF * (o.Cin + (o.src2_mode == VP_SRC2_CONCAT ? o.Cin2 : 0));
+    *engine = p->engines[i];
+  } else {
+    *M = (int64_t)o.B * o.Tin * o.Fin; *N = o.Cin; *K = 0;
   }
   return VP_OK;
 }

@@ -297,6 +297,19 @@ class Program:
             self._p, C.c_void_p(wave.data_ptr()), B, Lpad, kp, C.c_void_p(feats_scratch.data_ptr()),
             C.c_void_p(fe_scratch.data_ptr()), C.c_void_p(emb.data_ptr()), self.engine.stream_ptr()))
 
+    def run_profiled(self, feats, emb):
+        """vp_embed with per-op CUDA-event timing -> list of dicts (kind, M, N, K, engine, ms)."""
+        ms = (C.c_float * self.n_ops)()
+        _check(self.engine.handle, L.lib().vp_embed_profiled(self._p, C.c_void_p(feats.data_ptr()),
+                                                             C.c_void_p(emb.data_ptr()), self.engine.stream_ptr(), ms))
+        out = []
+        for i in range(self.n_ops):
+            kind, eng = C.c_int32(), C.c_int32()
+            M, N, K = C.c_int64(), C.c_int64(), C.c_int64()
+            L.lib().vp_program_op_info(self._p, i, C.byref(kind), C.byref(M), C.byref(N), C.byref(K), C.byref(eng))
+            out.append(dict(op=i, kind=kind.value, M=M.value, N=N.value, K=K.value, engine=eng.value, ms=float(ms[i])))
+        return out
+
     def peek(self, name):
         """Copy a tapped intermediate out of the workspace (tests only)."""
         view, rows = self.taps[name]

@@ -171,14 +171,18 @@ class MVectorPredictor:
             audio_segment.normalize(target_db=ds.target_dB)
         return audio_segment
 
-    def _embed_padded(self, inputs, lens_ratio):
-        """inputs: np.float32 [B, Lmax] zero padded -> np.float32 [B, embd_dim].  One H2D, one fused C-ABI call
-        (front-end + backbone), one D2H."""
-        B, Lp = inputs.shape
-        if self._pinned is None or self._pinned.numel() < inputs.size:
-            self._pinned = torch.empty(max(inputs.size, 1 << 20), dtype=torch.float32).pin_memory()
-        host = self._pinned[:inputs.size].view(B, Lp)
-        host.copy_(torch.from_numpy(inputs))
+    def _pinned_batch(self, B, Lp):
+        """Reusable pinned host staging buffer viewed as [B, Lp] float32."""
+        n = B * Lp
+        if self._pinned is None or self._pinned.numel() < n:
+            self._pinned = torch.empty(max(n, 1 << 20), dtype=torch.float32).pin_memory()
+        return self._pinned[:n].view(B, Lp)
+
+    def _embed_host(self, host, lens_ratio):
+        """host: pinned float32 [B, Lmax] (zero padded) -> np.float32 [B, embd_dim].  One H2D, ONE fused C-ABI call
+        (vp_embed_wave: front-end + CMN/mask + backbone), one D2H."""
+        from . import _lib as L
+        B, Lp = host.shape
         wave = host.to(self.device, non_blocking=True)
         fz = self._audio_featurizer
         T = fz.num_frames(Lp)
@@ -189,7 +193,6 @@ class MVectorPredictor:
             keep = fz.keep_frames(lens_ratio, T).to(self.device, non_blocking=True)
         prog = self.predictor.program(B, T)
         eng = fz.engine
-        from . import _lib as L
         feats = torch.empty(B * T * fz.feat_fun.n_mels, dtype=torch.float32, device=self.device)
         scratch = torch.empty(max(int(L.lib().vp_frontend_scratch_floats(eng.handle, B, Lp)), 1), dtype=torch.float32,
                               device=self.device)
@@ -200,19 +203,24 @@ class MVectorPredictor:
     def predict(self, audio_data, sample_rate=16000):
         """预测一个音频的特征 (predict.py:214-229) -> np.ndarray [embd_dim]"""
         seg = self._load_audio(audio_data=audio_data, sample_rate=sample_rate)
-        x = np.ascontiguousarray(seg.samples, dtype=np.float32)[None, :]
-        return self._embed_padded(x, None)[0]
+        host = self._pinned_batch(1, seg.samples.shape[0])
+        host[0].copy_(torch.from_numpy(np.ascontiguousarray(seg.samples, dtype=np.float32)))
+        return self._embed_host(host, None)[0]
 
     def predict_batch(self, audios_data, sample_rate=16000, batch_size=32):
         """预测一批音频的特征 (predict.py:231-265) -> np.ndarray [B, embd_dim], order preserved."""
         waves = [self._load_audio(audio_data=a, sample_rate=sample_rate).samples for a in audios_data]
         lmax = max(w.shape[0] for w in waves)
-        inputs = np.zeros((len(waves), lmax), dtype=np.float32)
+        host = self._pinned_batch(len(waves), lmax)
+        hnp = host.numpy()
         ratio = []
-        for i, w in enumerate(waves):
-            inputs[i, :w.shape[0]] = w
-            ratio.append(w.shape[0] / lmax)
-        return self._embed_padded(inputs, torch.tensor(ratio, dtype=torch.float32))
+        for i, w in enumerate(waves):                     # zero padding to the longest item (predict.py:248-254)
+            n = w.shape[0]
+            hnp[i, :n] = w
+            if n < lmax:
+                hnp[i, n:] = 0.0
+            ratio.append(n / lmax)
+        return self._embed_host(host, torch.tensor(ratio, dtype=torch.float32))
 
     def contrast(self, audio_data1, audio_data2):
         """声纹对比 (predict.py:267-279) -> cosine similarity"""
