@@ -140,7 +140,7 @@ FULL = [
 def test_full_size_models_vs_oracle(model, margs, fdim, B, T):
     """BASELINE.json model configurations at full width, seeded weights, features ~ CMN'd log-mel statistics."""
     from oracle import models as om
-    sd = om.random_state_dict(model, fdim, seed=3, **margs)
+    sd = om.random_state_dict(model, fdim, seed=3, gain=om.CONDITIONED_GAIN[model], **margs)
     g = torch.Generator().manual_seed(17)
     feats = torch.randn(B, T, fdim, generator=g) * 2.0
     ref = om.forward(model, sd, feats, **margs).numpy()
