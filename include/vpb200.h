@@ -119,6 +119,10 @@ typedef struct vp_op {
   int64_t src, src2, dst, res, gate, ubias;
   /* weight-arena operands: byte offsets (or -1) */
   int64_t w, bias, pre_s, pre_h, post_s, post_h;
+  /* optional tensor-core image of w (or -1): split-TF32 hi/lo planes, tiled [n_tile][k_block][hi|lo][tc_bn rows][32]
+   * floats with the 16-byte chunks of every 128-byte row XOR-swizzled by (row & 7) -- the UMMA SWIZZLE_128B K-major
+   * shared-memory image, so one bulk-async copy lands a pipeline stage (see conv_tc.cu, mvector/engine.py::pack_tc) */
+  int64_t w_tc;
   /* source geometry: rows = B*Tin*Fin, each row in_ld floats, channels [in_coff, in_coff+Cin) */
   int32_t Tin, Fin, Cin, in_ld, in_coff;
   int32_t src2_mode, src2_ld, src2_coff, Cin2;   /* ADD: same Cin; CONCAT: channels Cin..Cin+Cin2 come from src2 */
@@ -132,7 +136,8 @@ typedef struct vp_op {
   int32_t act, act2;       /* y = act2(act(acc + bias + ubias) * post_s + post_h) * gate + res)  -- see DESIGN.md */
   int32_t seg_len, n_seg;  /* gate / ubias / SEG_CONTEXT rows per utterance: row (b*n_seg + min(t/seg_len, n_seg-1)) */
   float   eps;
-  int32_t reserved[7];
+  int32_t tc_bn;           /* N tile of w_tc: 256 if Cout >= 256 else Cout rounded up to 16 */
+  int32_t reserved[6];
 } vp_op;
 
 /* Upload the packed fp32 weight arena (host pointer, copied to the device; replaces any previous arena). */

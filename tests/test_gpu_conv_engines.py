@@ -1,0 +1,109 @@
+"""Op-level GPU tests of the two conv engines (exact fp32 FFMA, tcgen05 split-TF32) against the fp64 numpy interpreter
+(tests/plan_sim.py), over the conv geometries the five backbones use."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_case(case, engine_id):
+    from mvector import _lib as L
+    from mvector.engine import Engine, PlanBuilder, Program, View, WeightArena
+    from plan_sim import Sim
+    rng = np.random.default_rng(case['seed'])
+    B, Tin, Fin, Cin = case['B'], case['Tin'], case.get('Fin', 1), case['Cin']
+    Tout, Fout, N = case['Tout'], case.get('Fout', 1), case['N']
+    KT, KF = case.get('KT', 1), case.get('KF', 1)
+    Cin2 = case.get('Cin2', 0)
+    src2_mode = case.get('src2_mode', L.SRC2_NONE)
+    cin_tot = Cin + (Cin2 if src2_mode == L.SRC2_CONCAT else 0)
+    K = KT * KF * cin_tot
+    rows_in, rows_out = B * Tin * Fin, B * Tout * Fout
+    n_seg = case.get('n_seg', 1)
+    # one wide input matrix: [x | x2 | res(out rows) | gate/ubias rows]
+    c_x2 = Cin
+    c_res = c_x2 + (Cin2 if src2_mode == L.SRC2_CONCAT else (Cin if src2_mode == L.SRC2_ADD else 0))
+    c_gu = c_res + (N if case.get('res') else 0)
+    width = c_gu + (2 * N if (case.get('gate') or case.get('ubias')) else 0)
+    width = (width + 3) // 4 * 4
+    rows = max(rows_in, rows_out, B * n_seg)
+    X = (rng.standard_normal((rows, width)) * case.get('scale', 1.0)).astype(np.float32)
+    arena = WeightArena()
+    W = rng.standard_normal((N, K)) / np.sqrt(K)
+    w = arena.add_conv('w', W)
+    bias = arena.add('b', rng.standard_normal(N) * 0.1) if case.get('bias') else -1
+    post = (arena.add('ps', rng.uniform(0.5, 1.5, N)), arena.add('ph', rng.standard_normal(N) * 0.2)) if case.get('post') else None
+    pre = (arena.add('qs', rng.uniform(0.5, 1.5, cin_tot)), arena.add('qh', rng.standard_normal(cin_tot) * 0.2)) if case.get('pre') else None
+    pb = PlanBuilder(B, engine_id)
+    pb.in_floats = rows * width
+    inp = View(L.BUF_INPUT, width, 0, width)
+    src = inp.cols(0, Cin)
+    src2 = None
+    if src2_mode == L.SRC2_ADD:
+        src2 = inp.cols(c_x2, Cin)
+    elif src2_mode == L.SRC2_CONCAT:
+        src2 = inp.cols(c_x2, Cin2)
+    res = inp.cols(c_res, N) if case.get('res') else None
+    gate = ubias = None
+    if case.get('gate'):
+        gate = pb.alloc(B * n_seg, N)
+        pb.ew(L.EW_COPY, inp.cols(c_gu, N), gate, 1).B = B * n_seg
+    if case.get('ubias'):
+        ubias = pb.alloc(B * n_seg, N)
+        pb.ew(L.EW_COPY, inp.cols(c_gu + N, N), ubias, 1).B = B * n_seg
+    out = pb.output_view(N, rows_out)
+    pb.conv(src, out, w, K, Tin, Tout, Fin=Fin, Fout=Fout, KT=KT, KF=KF, sT=case.get('sT', 1), sF=case.get('sF', 1),
+            dT=case.get('dT', 1), dF=1, padT=case.get('padT', 0), padF=case.get('padF', 0),
+            pad_mode=case.get('pad_mode', L.PAD_ZERO), bias=bias, pre=pre, pre_relu=bool(case.get('pre')), post=post,
+            act=case.get('act', L.ACT_NONE), act2=case.get('act2', L.ACT_NONE), res=res, gate=gate, ubias=ubias,
+            seg_len=case.get('seg_len'), n_seg=n_seg, src2=src2, src2_mode=src2_mode)
+    eng = Engine()
+    blob = arena.blob()
+    eng.load_weights(blob)
+    prog = Program(eng, pb)
+    y = torch.empty(rows_out, N, device='cuda')
+    prog.run(torch.from_numpy(X).cuda().contiguous(), y)
+    torch.cuda.synchronize()
+    ref = Sim(pb, blob, X).run().reshape(rows_out, N)
+    got = y.cpu().numpy()
+    eng.close()
+    return got, ref
+
+
+L_ = None
+CASES = dict(
+    gemm_512=dict(seed=1, B=8, Tin=298, Tout=298, Cin=512, N=512, bias=True, act=1, post=True),
+    gemm_n1536_k128=dict(seed=2, B=5, Tin=298, Tout=298, Cin=128, N=1536, bias=True),
+    gemm_k1536_n128_ubias_tanh=dict(seed=3, B=6, Tin=211, Tout=211, Cin=1536, N=128, ubias=True, act=1, post=True, act2=4),
+    res2_k3_dil2_reflect_add=dict(seed=4, B=9, Tin=298, Tout=298, Cin=64, N=64, KT=3, dT=2, padT=2, pad_mode=1, bias=True,
+                                  act=1, post=True, src2_mode=1),
+    stem_k5_reflect=dict(seed=5, B=7, Tin=298, Tout=298, Cin=80, N=512, KT=5, padT=2, pad_mode=1, bias=True, act=1, post=True),
+    tdnn_valid_k3_d3=dict(seed=6, B=4, Tin=300, Tout=294, Cin=512, N=512, KT=3, dT=3, bias=True, act=1, post=True),
+    conv2d_3x3_s2=dict(seed=7, B=3, Tin=61, Fin=40, Tout=31, Fout=20, Cin=32, N=48, KT=3, KF=3, sT=2, sF=2, padT=1, padF=1,
+                       bias=True, act=2),
+    conv2d_3x3_res_relu=dict(seed=8, B=2, Tin=50, Fin=20, Tout=50, Fout=20, Cin=32, N=32, KT=3, KF=3, padT=1, padF=1, bias=True,
+                             res=True, act2=1),
+    concat_1x1_silu=dict(seed=9, B=2, Tin=40, Fin=30, Tout=40, Fout=30, Cin=16, Cin2=16, N=16, bias=True, act=5, src2_mode=2),
+    cam_pre_bn_relu=dict(seed=10, B=6, Tin=149, Tout=149, Cin=160, N=128, pre=True, bias=True, act=1),
+    cam_local_gate_seg=dict(seed=11, B=6, Tin=249, Tout=249, Cin=128, N=32, KT=3, dT=2, padT=2, gate=True, seg_len=100, n_seg=3),
+    k5_stride2_zero=dict(seed=12, B=5, Tin=298, Tout=149, Cin=320, N=128, KT=5, sT=2, padT=2, bias=True, act=1),
+    n_tail_192=dict(seed=13, B=3, Tin=400, Tout=400, Cin=96, N=192, bias=True),
+    k_tail_72=dict(seed=14, B=11, Tin=100, Tout=100, Cin=24, N=24, KT=3, padT=1, bias=True, act=2),
+)
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_conv_ffma_engine_exact(name):
+    from mvector import _lib as L
+    got, ref = _run_case(CASES[name], L.ENGINE_FFMA)
+    assert np.abs(got - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_conv_tc_engine_split_tf32(name):
+    """tcgen05 split-TF32 engine: fp32-grade (error << single-pass TF32's ~1e-3)."""
+    from mvector import _lib as L
+    got, ref = _run_case(CASES[name], L.ENGINE_TC)
+    err = np.abs(got - ref).max() / max(1.0, np.abs(ref).max())
+    assert err <= 2e-5, err

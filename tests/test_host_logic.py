@@ -1,0 +1,157 @@
+"""Host-side logic that needs no GPU: C-ABI library loads and exports every symbol of include/vpb200.h, the tensor-core
+weight image packer, front-end constants, config surface, audio decoding, memory planner."""
+import ctypes
+import io
+import os
+import re
+import wave
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    lib_path = ge.build()
+    hdr = open(os.path.join(ROOT, 'include', 'vpb200.h')).read()
+    declared = set(re.findall(r'\b(vp_[a-z_0-9]+)\s*\(', hdr))
+    assert len(declared) >= 18
+    lib = ctypes.CDLL(lib_path)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f'{name} declared in vpb200.h but not exported by libvpb200.so'
+    from mvector import _lib
+    assert set(_lib.EXPORTS) == declared
+    L = _lib.lib()
+    assert L.vp_abi_version() == 1
+    assert L.vp_sizeof_op() == ctypes.sizeof(_lib.Op)
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from mvector.engine import Engine
+    from mvector.predict import MVectorPredictor
+    with pytest.raises(RuntimeError):
+        Engine()
+    with pytest.raises(AssertionError):
+        MVectorPredictor(configs={}, use_gpu=True)
+
+
+def test_pack_tc_image_roundtrip():
+    """Split-TF32 weight image: hi has a 10-bit mantissa, hi + lo == W exactly, and un-swizzling the SWIZZLE_128B
+    chunk permutation gives back the zero-padded [n_tile][k_block][BN][32] tiles."""
+    from mvector.engine import pack_tc, tc_tile_n, tf32_rna
+    rng = np.random.default_rng(0)
+    for N, K in ((512, 512), (192, 400), (128, 1536), (32, 384), (24, 72)):
+        W = rng.standard_normal((N, K)).astype(np.float32)
+        img, bn = pack_tc(W.astype(np.float64))
+        assert bn == tc_tile_n(N) and bn % 16 == 0 and bn <= 256
+        nt, kb = -(-N // bn), -(-K // 32)
+        t = img.reshape(nt, kb, 2, bn, 8, 4)
+        r = np.arange(bn)[:, None]
+        c = np.arange(8)[None, :]
+        un = t[:, :, :, r, c ^ (r & 7), :]                      # undo the XOR swizzle
+        un = un.reshape(nt, kb, 2, bn, 32)
+        hi = un[:, :, 0].transpose(0, 2, 1, 3).reshape(nt * bn, kb * 32)
+        lo = un[:, :, 1].transpose(0, 2, 1, 3).reshape(nt * bn, kb * 32)
+        assert np.array_equal(hi[:N, :K] + lo[:N, :K], W)
+        assert not (hi.view(np.uint32) & 0x1FFF).any()
+        assert np.all(hi[N:] == 0) and np.all(hi[:, K:] == 0) and np.all(lo[N:] == 0)
+        assert np.abs(lo[:N, :K]).max() <= np.abs(W).max() * 2.0 ** -11 * 1.01
+    x = np.float32([1.0 + 2.0 ** -11, 1.0 + 2.0 ** -11 + 2.0 ** -20, -(1.0 + 2.0 ** -11)])
+    assert np.array_equal(tf32_rna(x), np.float32([1.0 + 2.0 ** -10, 1.0 + 2.0 ** -10, -(1.0 + 2.0 ** -10)]))  # ties away
+
+
+def test_frontend_constants_match_oracle():
+    from mvector.data_utils.featurizer import KaldiFbank, MelSpectrogram
+    from oracle import frontend as ofe
+    kf = KaldiFbank(sample_frequency=16000, num_mel_bins=80)
+    assert (kf.n_fft, kf.win_length, kf.hop, kf.n_mels) == (512, 400, 160, 80)
+    assert np.array_equal(kf.window, ofe.feature_window('povey', 400).numpy())
+    dense = torch.nn.functional.pad(ofe.kaldi_mel_banks(80, 512, 16000.0, 20.0, 0.0), (0, 1)).numpy()
+    start, count, off, w = kf.bank
+    rec = np.zeros_like(dense)
+    for m in range(80):
+        rec[m, start[m]:start[m] + count[m]] = w[off[m]:off[m] + count[m]]
+    assert np.array_equal(rec, dense)
+    assert int(count.sum()) < 600                       # ~501 non-zeros
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ms = MelSpectrogram(sample_rate=16000, n_fft=1024, win_length=1024, hop_length=320, f_min=50.0, f_max=14000.0,
+                            n_mels=64)
+    fb = ofe.htk_mel_fbanks(513, 50.0, 14000.0, 64, 16000).numpy().T
+    start, count, off, w = ms.bank
+    rec = np.zeros_like(fb)
+    for m in range(64):
+        rec[m, start[m]:start[m] + count[m]] = w[off[m]:off[m] + count[m]]
+    assert np.array_equal(rec, fb)
+
+
+def test_featurizer_surface():
+    from mvector.data_utils.featurizer import AudioFeaturizer
+    fz = AudioFeaturizer('Fbank', method_args=dict(sample_frequency=16000, num_mel_bins=80))
+    assert fz.feature_dim == 80 and fz.num_frames(48000) == 298 and fz.num_frames(399) == 0
+    assert AudioFeaturizer('MelSpectrogram', method_args=dict(n_fft=512, n_mels=40)).feature_dim == 40
+    # mask_lens = round(ratio * T) in float32, half to even (featurizer.py:82-84)
+    assert fz.keep_frames([16000 / 48000, 1.0, 0.5], 298).tolist() == [99, 298, 149]
+    assert fz.keep_frames([0.5], 297).tolist() == [148]
+    with pytest.raises(TypeError):
+        AudioFeaturizer('Fbank', method_args=dict(bogus=1))
+    with pytest.raises(NotImplementedError):
+        AudioFeaturizer('MFCC')
+    with pytest.raises(Exception):
+        AudioFeaturizer('Nope')
+
+
+def test_audio_segment_wav_and_normalize():
+    from mvector.audio import AudioSegment
+    pcm = (np.sin(np.arange(16000) * 0.05) * 8000).astype('<i2')
+    buf = io.BytesIO()
+    with wave.open(buf, 'wb') as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000); w.writeframes(pcm.tobytes())
+    seg = AudioSegment.from_bytes(buf.getvalue())
+    assert seg.sample_rate == 16000 and abs(seg.duration - 1.0) < 1e-9
+    assert np.array_equal(seg.samples, pcm.astype(np.float32) / 32768.0)
+    seg.normalize(target_db=-20)
+    assert abs(seg.rms_db - (-20)) < 1e-3
+    seg.resample(8000)
+    assert seg.sample_rate == 8000 and abs(seg.samples.shape[0] - 8000) <= 1
+
+
+def test_memory_planner_reuses_and_never_overlaps_live_buffers():
+    from mvector.engine import PlanBuilder
+    pb = PlanBuilder(1)
+    live = {}
+    rng = np.random.default_rng(1)
+    for step in range(300):
+        if live and rng.random() < 0.45:
+            k = list(live)[rng.integers(len(live))]
+            pb.free(live.pop(k))
+        else:
+            v = pb.alloc(int(rng.integers(1, 2000)), int(rng.integers(1, 64)) * 4)
+            live[v.off] = v
+        iv = sorted((v.off, v.off + pb._live[v.off]) for v in live.values())
+        for (a0, a1), (b0, b1) in zip(iv, iv[1:]):
+            assert a1 <= b0
+        assert all(e <= pb.peak for _, e in iv)
+    assert pb.peak < 300 * 2000 * 256 * 4 / 4            # reuse happened
+
+
+def test_default_model_plans_lower_and_fit(manifest):
+    """Every BASELINE configuration lowers on the host; report op counts / workspace."""
+    from mvector.models import build_model
+    from mvector.utils.utils import dict_to_object
+    from oracle import models as om
+    cases = [('EcapaTdnn', 80, dict(embd_dim=192, pooling_type='ASP', channels=[512, 512, 512, 512, 1536]), 256, 298),
+             ('CAMPPlus', 80, dict(embd_dim=192), 256, 298),
+             ('TDNN', 80, dict(embd_dim=192, channels=512, pooling_type='ASP'), 1, 365)]
+    for name, fdim, margs, B, T in cases:
+        m = build_model(fdim, dict_to_object({'model_conf': {'model': name, 'model_args': margs}}))
+        m.load_state_dict(om.random_state_dict(name, fdim, seed=0, **margs))
+        pb = m.lower(B, T)
+        assert pb.in_floats == B * T * fdim and pb.out_floats == B * 192
+        assert pb.peak < 40 * 2 ** 30

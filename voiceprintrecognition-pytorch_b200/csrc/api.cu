@@ -270,6 +270,12 @@ static int validate_op(vp_program* p, const vp_op& o, int i) {
       if (o.res != VP_BUF_NONE) TRY(check_act_buf(p, "res", o.res, view_floats(rows_out, o.res_ld, o.res_coff, o.Cout), false, i));
       if (o.gate != VP_BUF_NONE) TRY(check_act_buf(p, "gate", o.gate, (size_t)o.B * o.n_seg * o.Cout, false, i));
       if (o.ubias != VP_BUF_NONE) TRY(check_act_buf(p, "ubias", o.ubias, (size_t)o.B * o.n_seg * o.Cout, false, i));
+      if (o.w_tc >= 0) {
+        if (o.kind != VP_OP_CONV || o.tc_bn < 16 || o.tc_bn > 256 || (o.tc_bn & 15)) return fail(h, VP_ERR_INVALID, "op %d: tc_bn", i);
+        const size_t nt = (o.Cout + o.tc_bn - 1) / o.tc_bn, kb = ((size_t)o.KT * o.KF * cin_tot + 31) / 32;
+        if (o.w_tc & 127) return fail(h, VP_ERR_INVALID, "op %d: w_tc must be 128 B aligned", i);
+        TRY(check_w(p, "w_tc", o.w_tc, nt * kb * 2 * (size_t)o.tc_bn * 32, i));
+      }
       if (o.bias >= 0) TRY(check_w(p, "bias", o.bias, o.Cout, i));
       if (o.pre_s >= 0) { TRY(check_w(p, "pre_s", o.pre_s, cin_tot, i)); TRY(check_w(p, "pre_h", o.pre_h, cin_tot, i)); }
       if (o.post_s >= 0) { TRY(check_w(p, "post_s", o.post_s, o.Cout, i)); TRY(check_w(p, "post_h", o.post_h, o.Cout, i)); }
@@ -390,7 +396,7 @@ static void fill_conv(const vp_program* p, const vp_op& o, const float* feats, f
   c.src2 = o.src2_mode == VP_SRC2_NONE ? nullptr : rd(p, o.src2, feats, emb);
   c.dst = const_cast<float*>(rd(p, o.dst, feats, emb));
   c.res = rd(p, o.res, feats, emb); c.gate = rd(p, o.gate, feats, emb); c.ubias = rd(p, o.ubias, feats, emb);
-  c.w = wt(p, o.w); c.bias = wt(p, o.bias); c.pre_s = wt(p, o.pre_s); c.pre_h = wt(p, o.pre_h);
+  c.w = wt(p, o.w); c.w_tc = wt(p, o.w_tc); c.tc_bn = o.tc_bn; c.bias = wt(p, o.bias); c.pre_s = wt(p, o.pre_s); c.pre_h = wt(p, o.pre_h);
   c.post_s = wt(p, o.post_s); c.post_h = wt(p, o.post_h);
   c.B = o.B; c.Tin = o.Tin; c.Fin = o.Fin; c.Cin = o.Cin;
   c.CinTot = o.Cin + (o.src2_mode == VP_SRC2_CONCAT ? o.Cin2 : 0);

@@ -9,13 +9,13 @@ namespace vpb {
 // Resolved (device-pointer) form of a vp_op, passed to kernels by value.
 struct ConvParams {
   const float* src; const float* src2; float* dst; const float* res; const float* gate; const float* ubias;
-  const float* w; const float* bias; const float* pre_s; const float* pre_h; const float* post_s; const float* post_h;
+  const float* w; const float* w_tc; const float* bias; const float* pre_s; const float* pre_h; const float* post_s; const float* post_h;
   int M, N, K;                       // M = B*Tout*Fout rows, N = Cout, K = KT*KF*CinTot
   int B, Tin, Fin, Cin, CinTot, in_ld, in_coff;
   int src2_mode, src2_ld, src2_coff;
   int Tout, Fout, out_ld, out_coff, res_ld, res_coff;
   int KT, KF, sT, sF, dT, dF, padT, padF, pad_mode;
-  int w_ld, pre_relu, act, act2, seg_len, n_seg;
+  int w_ld, pre_relu, act, act2, seg_len, n_seg, tc_bn;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {

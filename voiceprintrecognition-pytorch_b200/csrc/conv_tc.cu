@@ -1,6 +1,329 @@
-// tcgen05 engine placeholder (filled in by the 3xTF32 UMMA kernel).
+// tcgen05 engine: implicit-GEMM convolution on the 5th-gen tensor cores with fp32-grade accuracy (split TF32, "3xTF32").
+//
+//   out[m, n] = epi( sum_k A(m, k) * W[n, k] )        same op contract as conv_ffma.cu (common.cuh::ConvParams)
+//
+// Why split TF32: a single TF32 (or BF16) pass breaks the 1e-4 embedding parity gate (3e-4 / 2.7e-3),
+// so every operand is split  x = hi + lo,  hi = tf32(x),  lo = x - hi  and three MMAs are accumulated in fp32 TMEM:
+//   D += A_lo * B_hi;  D += A_hi * B_lo;  D += A_hi * B_hi        (the dropped lo*lo term is ~2^-22 relative).
+//
+// Persistent, warp-specialised CTA (320 threads), one CTA per SM:
+//   warps 0-3  epilogue   : tcgen05.ld accumulator rows from TMEM -> fused epilogue (bias / ubias / act / BN affine /
+//                           gate / residual / act2) -> float4 stores; TMEM accumulators are double buffered so the
+//                           epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 4-7  A producers: gather the implicit-GEMM A tile straight from the channel-last activation map (any tap /
+//                           dilation / stride / reflect or zero padding / add or concat second source / BN-ReLU
+//                           prologue: common.cuh::gather_a4) with coalesced 128 B row segments, split into hi / lo and
+//                           write both in the UMMA K-major SWIZZLE_128B shared-memory layout
+//   warp 8     B loader   : weights are pre-split and pre-tiled on the host in exactly that shared-memory image, so one
+//                           bulk-async copy (TMA engine, cp.async.bulk -> UBLKCP) per stage lands B_hi|B_lo
+//   warp 9     MMA issuer : one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8), commits to mbarriers
+// Pipeline: S shared-memory stages (full/empty mbarriers) + 2 TMEM accumulator buffers (tmem_full/tmem_empty).
 #include "kernels.cuh"
+
 namespace vpb {
-bool conv_tc_supported(const ConvParams&) { return false; }
-cudaError_t launch_conv_tc(const ConvParams&, cudaStream_t) { return cudaErrorNotSupported; }
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                  // fp32 elements per stage row = 128 B = one SWIZZLE_128B row
+constexpr int A_TILE = BM * BK * 4;     // 16 KB per (hi|lo) A tile
+constexpr int NUM_THREADS = 320;
+constexpr int PRODUCER_THREADS = 128;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 (16 B) |
+// SBO = 1024 B (8 rows x 128 B) | version 1 (sm_100) | layout type 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct TcArgs {
+  const float* w_tc;     // pre-split, pre-tiled, pre-swizzled weights: [n_tile][k_block][hi BN x 128 B | lo BN x 128 B]
+  int BN;                // N tile (multiple of 16, <= 256)
+  int stages;
+  int tmem_cols;         // power of two >= 2*BN
+  int m_tiles, n_tiles, k_blocks;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p,
+                                                                 const __grid_constant__ TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(8) uint64_t bars[2 * 8 + 4];     // full[S], empty[S], tmem_full[2], tmem_empty[2]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int BN = a.BN;
+  const uint32_t b_tile = (uint32_t)BN * 128u;                 // bytes of one (hi|lo) B tile
+  const uint32_t stage_bytes = 2u * A_TILE + 2u * b_tile;
+  const int S = a.stages;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]);
+  const uint32_t tfull0 = smem_u32(&bars[16]), tempty0 = smem_u32(&bars[18]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full0 + 8 * s, PRODUCER_THREADS + 1);          // 128 A-producer arrivals + 1 expect_tx arrival (B)
+      mbar_init(empty0 + 8 * s, 1);                            // one tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull0 + 8 * i, 1);
+      mbar_init(tempty0 + 8 * i, 128);                         // 128 epilogue threads
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int total_tiles = a.m_tiles * a.n_tiles;
+
+  if (warp >= 4 && warp < 8) {
+    // =========================== A producers ===========================
+    const int t = threadIdx.x - 128;       // 0..127
+    const int chunk = t & 7;               // 16-byte chunk inside the 128-byte K row
+    const int r0 = t >> 3;                 // rows r0 + 16*i
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / a.n_tiles) * BM;
+      RowInfo rows[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rows[i] = decode_row(p, m0 + r0 + 16 * i);
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = gather_a4(p, rows[i], chunk * 4);
+      for (int kb = 0; kb < a.k_blocks; ++kb, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const uint32_t a_hi = smem_base + s * stage_bytes;
+        const uint32_t a_lo = a_hi + A_TILE;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + 16 * i;
+          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+          float4 hi, lo;
+          hi.x = tf32_rna(v[i].x); hi.y = tf32_rna(v[i].y); hi.z = tf32_rna(v[i].z); hi.w = tf32_rna(v[i].w);
+          lo.x = v[i].x - hi.x; lo.y = v[i].y - hi.y; lo.z = v[i].z - hi.z; lo.w = v[i].w - hi.w;
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+        }
+        fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(full0 + 8 * s);
+        if (kb + 1 < a.k_blocks) {           // prefetch the next K block into registers while this one is consumed
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = gather_a4(p, rows[i], (kb + 1) * BK + chunk * 4);
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // =========================== B loader (bulk async copy) ===========================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % a.n_tiles;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.w_tc) + (size_t)nt * a.k_blocks * (2u * b_tile);
+        for (int kb = 0; kb < a.k_blocks; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          mbar_expect_tx(full0 + 8 * s, 2u * b_tile);
+          bulk_copy_g2s(smem_base + s * stage_bytes + 2u * A_TILE, src + (size_t)kb * (2u * b_tile), 2u * b_tile,
+                        full0 + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      // kind::tf32 instruction descriptor: D=F32 (bit 4), A=B=TF32 (2 at bits 7 and 10), K-major, N>>3 @17, M>>4 @24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const int acc = tcount & 1;
+        mbar_wait(tempty0 + 8 * acc, ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < a.k_blocks; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(full0 + 8 * s, (it / S) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_base + s * stage_bytes, a_lo = a_hi + A_TILE;
+          const uint32_t b_hi = a_hi + 2u * A_TILE, b_lo = b_hi + b_tile;
+#pragma unroll
+          for (int kc = 0; kc < BK / 8; ++kc) {               // UMMA_K = 8 for tf32 = 32 bytes inside the swizzle row
+            const uint64_t dah = smem_desc(a_hi + kc * 32), dal = smem_desc(a_lo + kc * 32);
+            const uint64_t dbh = smem_desc(b_hi + kc * 32), dbl = smem_desc(b_lo + kc * 32);
+            umma_tf32(d, dal, dbh, idesc, (kb | kc) != 0);
+            umma_tf32(d, dah, dbl, idesc, 1);
+            umma_tf32(d, dah, dbh, idesc, 1);
+          }
+          umma_commit(empty0 + 8 * s);                        // frees the smem stage when these MMAs retire
+        }
+        umma_commit(tfull0 + 8 * acc);                        // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 0-3 <-> TMEM lanes 32*warp ..) ===========================
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int acc = tcount & 1;
+      const int m = (tile / a.n_tiles) * BM + warp * 32 + lane;
+      const int n0 = (tile % a.n_tiles) * BN;
+      mbar_wait(tfull0 + 8 * acc, (tcount >> 1) & 1);
+      tc_fence_after();
+      const bool mok = m < p.M;
+      const int urow = mok ? urow_of(p, m) : 0;
+      float* orow = p.dst + (size_t)(mok ? m : 0) * p.out_ld + p.out_coff;
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+        if (mok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int n = n0 + c0 + j;
+            if (n + 3 < p.N) {
+              float4 o;
+              o.x = epilogue1(p, v[j + 0], m, n + 0, urow);
+              o.y = epilogue1(p, v[j + 1], m, n + 1, urow);
+              o.z = epilogue1(p, v[j + 2], m, n + 2, urow);
+              o.w = epilogue1(p, v[j + 3], m, n + 3, urow);
+              *reinterpret_cast<float4*>(orow + n) = o;
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (n + q < p.N) orow[n + q] = epilogue1(p, v[j + q], m, n + q, urow);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty0 + 8 * acc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
+  }
+}
+
+}  // namespace tc
+
+// Host-visible tiling rule (mirrored by the Python packer mvector/engine.py::tc_tile_n).
+static int tc_tile_n(int N) {
+  if (N >= 256) return 256;
+  return (N + 15) & ~15;
+}
+
+bool conv_tc_supported(const ConvParams& p) {
+  if (p.w_tc == nullptr) return false;
+  if (p.M < 1024) return false;                       // tiny-M ops (SE / ASP bias / final FC) stay on the exact FFMA engine
+  if (p.N < 16 || (p.N & 3) || (p.K & 3)) return false;
+  if (p.tc_bn != tc_tile_n(p.N)) return false;
+  return true;
+}
+
+cudaError_t launch_conv_tc(const ConvParams& p, cudaStream_t stream) {
+  using namespace tc;
+  TcArgs a;
+  a.w_tc = p.w_tc;
+  a.BN = p.tc_bn;
+  const int stage_bytes = 2 * A_TILE + 2 * a.BN * 128;
+  a.stages = SMEM_BUDGET / stage_bytes;
+  if (a.stages > 8) a.stages = 8;
+  if (a.stages < 2) return cudaErrorInvalidConfiguration;
+  int cols = 32;
+  while (cols < 2 * a.BN) cols <<= 1;
+  a.tmem_cols = cols;
+  a.m_tiles = (p.M + BM - 1) / BM;
+  a.n_tiles = (p.N + a.BN - 1) / a.BN;
+  a.k_blocks = (p.K + BK - 1) / BK;
+  const size_t smem = (size_t)a.stages * stage_bytes + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = a.m_tiles * a.n_tiles;
+  const int grid = tiles < sms ? tiles : sms;
+  conv_tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(p, a);
+  return cudaGetLastError();
+}
+
 }  // namespace vpb

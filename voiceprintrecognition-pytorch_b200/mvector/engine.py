@@ -78,8 +78,49 @@ class WeightArena:
         self.index[name] = (off, a.size)
         return off
 
+    def add_conv(self, name, W2d, tc=True):
+        """A conv/linear weight [N, K] (K ordered (tap, ci)): the plain fp32 matrix (exact FFMA engine) plus, for layers
+        that can run on the tensor cores, its split-TF32 pre-tiled shared-memory image (conv_tc.cu)."""
+        W2d = np.asarray(W2d, dtype=np.float64)
+        d = {'w': self.add(name, W2d)}
+        if tc and W2d.shape[0] >= 16 and W2d.shape[0] % 4 == 0 and W2d.shape[1] % 4 == 0:
+            img, bn = pack_tc(W2d)
+            d['w_tc'] = self.add(name + '.tc', img)
+            d['tc_bn'] = bn
+        return d
+
     def blob(self):
         return np.concatenate(self._chunks) if self._chunks else np.zeros(64, dtype=np.float32)
+
+
+def tc_tile_n(N):
+    """N tile of the tcgen05 engine (must match conv_tc.cu::tc_tile_n)."""
+    return 256 if N >= 256 else (N + 15) // 16 * 16
+
+
+def tf32_rna(x):
+    """cvt.rna.tf32.f32: round-to-nearest, ties away from zero, to a 10-bit mantissa (fp32 container)."""
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def pack_tc(W):
+    """[N, K] -> (float32 image [n_tiles, k_blocks, 2(hi|lo), BN, 32] with SWIZZLE_128B chunk permutation, BN).
+    hi = tf32(W), lo = W - hi (exact in fp32).  Rows >= N / columns >= K are zero."""
+    N, K = W.shape
+    bn = tc_tile_n(N)
+    nt, kb = (N + bn - 1) // bn, (K + 31) // 32
+    Wp = np.zeros((nt * bn, kb * 32), dtype=np.float32)
+    Wp[:N, :K] = W.astype(np.float32)
+    hi = tf32_rna(Wp)
+    lo = (Wp - hi).astype(np.float32)
+    img = np.stack([hi, lo], axis=0).reshape(2, nt, bn, kb, 8, 4)          # [p, nt, r, kb, chunk, 4]
+    img = img.transpose(1, 3, 0, 2, 4, 5)                                  # [nt, kb, p, r, chunk, 4]
+    r = np.arange(bn)[:, None]
+    c = np.arange(8)[None, :]
+    out = np.empty_like(img)
+    out[:, :, :, r, c ^ (r & 7), :] = img[:, :, :, r, c, :]
+    return np.ascontiguousarray(out).reshape(-1), bn
 
 
 class View:
@@ -163,7 +204,7 @@ class PlanBuilder:
         o = L.Op()
         o.kind = kind
         o.B = self.B
-        for f in ('src', 'src2', 'dst', 'res', 'gate', 'ubias', 'w', 'bias', 'pre_s', 'pre_h', 'post_s', 'post_h'):
+        for f in ('src', 'src2', 'dst', 'res', 'gate', 'ubias', 'w', 'bias', 'pre_s', 'pre_h', 'post_s', 'post_h', 'w_tc'):
             setattr(o, f, -1)
         o.Fin = o.Fout = 1
         o.KT = o.KF = o.sT = o.sF = o.dT = o.dF = 1
@@ -182,7 +223,11 @@ class PlanBuilder:
         o.dst, o.out_ld, o.out_coff, o.Cout = dst.off, dst.ld, dst.coff, dst.C
         o.Tin, o.Fin, o.Tout, o.Fout = Tin, Fin, Tout, Fout
         o.KT, o.KF, o.sT, o.sF, o.dT, o.dF, o.padT, o.padF, o.pad_mode = KT, KF, sT, sF, dT, dF, padT, padF, pad_mode
-        o.w, o.w_ld, o.bias = w, w_ld, bias
+        if isinstance(w, dict):            # packed by WeightArena.add_conv: plain + optional tensor-core image
+            o.w, o.w_tc, o.tc_bn = w['w'], w.get('w_tc', -1), w.get('tc_bn', 0)
+        else:
+            o.w = w
+        o.w_ld, o.bias = w_ld, bias
         if pre is not None:
             o.pre_s, o.pre_h = pre
             o.pre_relu = 1 if pre_relu else 0

@@ -81,7 +81,7 @@ class CAMPPlus(Backbone):
 
         def cb(name, conv_key, bn):
             W, b = fold_conv_bn(sd, conv_key, bn)
-            o[name] = dict(w=arena.add(name + '.w', W), b=arena.add(name + '.b', b))
+            o[name] = dict(w=arena.add_conv(name + '.w', W), b=arena.add(name + '.b', b))
 
         W, b = fold_conv_bn(sd, 'head.conv1.weight', 'head.bn1')        # [32, (kt,kf,1)] -> 9 taps
         o['stem'] = dict(w=arena.add('stem.w', W), b=arena.add('stem.b', b))
@@ -97,7 +97,7 @@ class CAMPPlus(Backbone):
         perm = fc_perm(self.F8, self.m)
         Wt = _np64(sd['xvector.tdnn.linear.weight'])[:, perm, :]             # [N, mycol, kt]
         s, h = bn_affine(sd, 'xvector.tdnn.nonlinear.batchnorm')
-        o['tdnn'] = dict(w=arena.add('tdnn.w', conv1d_weight(Wt) * s[:, None]), b=arena.add('tdnn.b', h))
+        o['tdnn'] = dict(w=arena.add_conv('tdnn.w', conv1d_weight(Wt) * s[:, None]), b=arena.add('tdnn.b', h))
         for bi, (nl, k, dil) in enumerate(_BLOCKS, start=1):
             for li in range(nl):
                 p = f'xvector.block{bi}.tdnnd{li + 1}'
@@ -105,9 +105,9 @@ class CAMPPlus(Backbone):
                 s2, h2 = bn_affine(sd, p + '.nonlinear2.batchnorm')
                 o[p] = dict(
                     pre_s=arena.add(p + '.pre_s', s1), pre_h=arena.add(p + '.pre_h', h1),
-                    w1=arena.add(p + '.w1', _np64(sd[p + '.linear1.weight'])[:, :, 0] * s2[:, None]),
+                    w1=arena.add_conv(p + '.w1', _np64(sd[p + '.linear1.weight'])[:, :, 0] * s2[:, None]),
                     b1=arena.add(p + '.b1', h2),
-                    wl=arena.add(p + '.wl', conv1d_weight(sd[p + '.cam_layer.linear_local.weight'])),
+                    wl=arena.add_conv(p + '.wl', conv1d_weight(sd[p + '.cam_layer.linear_local.weight'])),
                     wa=arena.add(p + '.wa', _np64(sd[p + '.cam_layer.linear1.weight'])[:, :, 0]),
                     ba=arena.add(p + '.ba', sd[p + '.cam_layer.linear1.bias']),
                     wb=arena.add(p + '.wb', _np64(sd[p + '.cam_layer.linear2.weight'])[:, :, 0]),
@@ -115,7 +115,7 @@ class CAMPPlus(Backbone):
             p = f'xvector.transit{bi}'
             s, h = bn_affine(sd, p + '.nonlinear.batchnorm')
             o[p] = dict(pre_s=arena.add(p + '.pre_s', s), pre_h=arena.add(p + '.pre_h', h),
-                        w=arena.add(p + '.w', _np64(sd[p + '.linear.weight'])[:, :, 0]))
+                        w=arena.add_conv(p + '.w', _np64(sd[p + '.linear.weight'])[:, :, 0]))
         s, h = bn_affine(sd, 'xvector.out_nonlinear.batchnorm')
         o['out_bn'] = (arena.add('out_bn.s', s), arena.add('out_bn.h', h))
         s, h = bn_affine(sd, 'xvector.dense.nonlinear.batchnorm')

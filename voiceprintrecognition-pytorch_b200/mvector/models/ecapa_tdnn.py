@@ -82,7 +82,7 @@ class EcapaTdnn(Backbone):
     # ---- weights ----
     def _pack_tdnn_block(self, sd, p, arena):
         s, h = bn_affine(sd, p + '.norm.norm')
-        return dict(w=arena.add(p + '.w', conv1d_weight(sd[p + '.conv.conv.weight'])),
+        return dict(w=arena.add_conv(p + '.w', conv1d_weight(sd[p + '.conv.conv.weight'])),
                     b=arena.add(p + '.b', sd[p + '.conv.conv.bias']),
                     s=arena.add(p + '.bn_s', s), h=arena.add(p + '.bn_h', h))
 
@@ -101,7 +101,7 @@ class EcapaTdnn(Backbone):
                        se_w2=arena.add(p + '.se.w2', _np64(sd[p + '.se_block.conv2.conv.weight'])[:, :, 0]),
                        se_b2=arena.add(p + '.se.b2', sd[p + '.se_block.conv2.conv.bias']))
             if (p + '.shortcut.conv.weight') in sd:
-                blk['sc_w'] = arena.add(p + '.sc.w', _np64(sd[p + '.shortcut.conv.weight'])[:, :, 0])
+                blk['sc_w'] = arena.add_conv(p + '.sc.w', _np64(sd[p + '.shortcut.conv.weight'])[:, :, 0])
                 blk['sc_b'] = arena.add(p + '.sc.b', sd[p + '.shortcut.conv.bias'])
             o[p] = blk
         o['mfa'] = self._pack_tdnn_block(sd, 'mfa', arena)

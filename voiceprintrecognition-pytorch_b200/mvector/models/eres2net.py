@@ -92,7 +92,7 @@ class ERes2Net(Backbone):
     def _pack_aff(self, sd, p, arena):
         W0, b0 = fold_conv_bn(sd, p + '.local_att.0.weight', p + '.local_att.1', p + '.local_att.0.bias')
         W1, b1 = fold_conv_bn(sd, p + '.local_att.3.weight', p + '.local_att.4', p + '.local_att.3.bias')
-        return dict(w0=arena.add(p + '.w0', W0), b0=arena.add(p + '.b0', b0), w1=arena.add(p + '.w1', W1),
+        return dict(w0=arena.add_conv(p + '.w0', W0), b0=arena.add(p + '.b0', b0), w1=arena.add_conv(p + '.w1', W1),
                     b1=arena.add(p + '.b1', b1), inter=W0.shape[0], ch=W1.shape[0])
 
     def _pack(self, sd, arena):
@@ -100,7 +100,7 @@ class ERes2Net(Backbone):
 
         def cb(name, conv_key, bn):
             W, b = fold_conv_bn(sd, conv_key, bn)
-            o[name] = dict(w=arena.add(name + '.w', W), b=arena.add(name + '.b', b))
+            o[name] = dict(w=arena.add_conv(name + '.w', W), b=arena.add(name + '.b', b))
 
         cb('stem', 'conv1.weight', 'bn1')
         for p, li, inpl, planes, w, stride, fuse, sc in self._blocks():
@@ -114,7 +114,7 @@ class ERes2Net(Backbone):
             if sc:
                 cb(p + '.sc', p + '.shortcut.0.weight', p + '.shortcut.1')
         for nm in ('layer1_downsample', 'layer2_downsample', 'layer3_downsample'):
-            o[nm] = arena.add(nm + '.w', conv2d_weight(sd[nm + '.weight']))
+            o[nm] = arena.add_conv(nm + '.w', conv2d_weight(sd[nm + '.weight']))
         for nm in ('fuse_mode12', 'fuse_mode123', 'fuse_mode1234'):
             o[nm] = self._pack_aff(sd, nm, arena)
         C4 = self.m * 8 * self.expansion

@@ -36,9 +36,10 @@ def pack_asp(sd, p, arena, C, perm=None):
         Wc, bc = Wc[perm], bc[perm]
     s, h = bn_affine(sd, p + '.tdnn.norm.norm')
     return dict(A=A, C=C,
-                w=arena.add(p + '.tdnn.w', W), b=arena.add(p + '.tdnn.b', sd[p + '.tdnn.conv.conv.bias']),
+                wx=arena.add_conv(p + '.tdnn.wx', W[:, :C]), wms=arena.add(p + '.tdnn.wms', W[:, C:]),
+                b=arena.add(p + '.tdnn.b', sd[p + '.tdnn.conv.conv.bias']),
                 s=arena.add(p + '.tdnn.bn_s', s), h=arena.add(p + '.tdnn.bn_h', h),
-                wc=arena.add(p + '.conv.w', Wc), bc=arena.add(p + '.conv.b', bc))
+                wc=arena.add_conv(p + '.conv.w', Wc), bc=arena.add(p + '.conv.b', bc))
 
 
 def lower_asp(pb, o, x, B, T, pooled):
@@ -47,9 +48,9 @@ def lower_asp(pb, o, x, B, T, pooled):
     stats = pb.alloc(B, 2 * C)
     pb.colstats(x, stats, T, L.STATS_MEAN_STD_CLAMP, eps=1e-12)
     ub = pb.alloc(B, A)
-    pb.conv(stats, ub, o['w'] + 4 * C, 3 * C, 1, 1, bias=o['b'], engine=L.ENGINE_FFMA)
+    pb.conv(stats, ub, o['wms'], 2 * C, 1, 1, bias=o['b'], engine=L.ENGINE_FFMA)
     h = pb.alloc(B * T, A)
-    pb.conv(x, h, o['w'], 3 * C, T, T, ubias=ub, act=L.ACT_RELU, post=(o['s'], o['h']), act2=L.ACT_TANH)
+    pb.conv(x, h, o['wx'], C, T, T, ubias=ub, act=L.ACT_RELU, post=(o['s'], o['h']), act2=L.ACT_TANH)
     logits = pb.alloc(B * T, C)
     pb.conv(h, logits, o['wc'], A, T, T, bias=o['bc'])
     pb.asp_pool(x, logits, pooled, T, eps=1e-12)

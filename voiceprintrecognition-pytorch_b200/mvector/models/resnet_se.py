@@ -69,7 +69,7 @@ class ResNetSE(Backbone):
 
         def cb(name, conv_key, bn):
             W, b = fold_conv_bn(sd, conv_key, bn)
-            o[name] = dict(w=arena.add(name + '.w', W), b=arena.add(name + '.b', b))
+            o[name] = dict(w=arena.add_conv(name + '.w', W), b=arena.add(name + '.b', b))
 
         cb('stem', 'conv1.weight', 'bn1')
         for p, inpl, planes, stride, ds in self._blocks():

@@ -47,7 +47,7 @@ class TDNN(Backbone):
     def _pack(self, sd, arena):
         o = self._off
         for i in range(1, 6):
-            e = dict(w=arena.add(f'td{i}.w', conv1d_weight(sd[f'td_layer{i}.weight'])),
+            e = dict(w=arena.add_conv(f'td{i}.w', conv1d_weight(sd[f'td_layer{i}.weight'])),
                      b=arena.add(f'td{i}.b', sd[f'td_layer{i}.bias']))
             if i < 5:
                 s, h = bn_affine(sd, f'bn{i}')
