@@ -286,6 +286,9 @@ def run_gpu_arm(args):
         for a in acc:
             a['ms'] /= nprof
         total = sum(a['ms'] for a in acc)
+        if args.dump_ops:
+            with open(args.dump_ops, 'w') as f:
+                json.dump(acc, f, indent=0)
         conv = [a for a in acc if a['kind'] == L.OP_CONV and a['K'] > 0]
         top = max(conv, key=lambda a: a['ms'])
         peaks = {}
@@ -347,6 +350,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--dump-ops', default=None, help='write the per-op device-time profile (JSON) to this path')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

@@ -140,8 +140,57 @@ __global__ void __launch_bounds__(256, 2) conv_ffma_kernel(const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Small-M linear layers (SE excitation MLPs, the ASP per-utterance bias, the final embedding FC, CAM++ context MLPs):
+// M <= 1024 rows but K up to 3072.  The tiled kernel above would run them on a handful of CTAs with a long serial K
+// loop; here one warp owns (row m, 32 output columns), lanes stride over K with coalesced 128 B loads of x and of
+// each weight row, then a fixed-order butterfly reduction -> deterministic.  grid = (ceil(N/32), ceil(M/8)).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) linear_small_m_kernel(const __grid_constant__ ConvParams p) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int m = blockIdx.y * 8 + wid;
+  const int n0 = blockIdx.x * 32;
+  if (m >= p.M) return;
+  const float* x = p.src + (size_t)m * p.in_ld + p.in_coff;      // pointwise, stride 1: source row == output row
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  for (int k = lane * 4; k < p.K; k += 128) {
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + k));
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (n0 + j < p.N) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)(n0 + j) * p.w_ld + k));
+        acc[j] = fmaf(xv.x, wv.x, acc[j]);
+        acc[j] = fmaf(xv.y, wv.y, acc[j]);
+        acc[j] = fmaf(xv.z, wv.z, acc[j]);
+        acc[j] = fmaf(xv.w, wv.w, acc[j]);
+      }
+    }
+  }
+  // transpose-reduce: after the butterfly lane j holds the total of column j
+  float mine = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float t = warp_sum(acc[j]);
+    if (lane == j) mine = t;
+  }
+  const int n = n0 + lane;
+  if (n < p.N) p.dst[(size_t)m * p.out_ld + p.out_coff + n] = epilogue1(p, mine, m, n, urow_of(p, m));
+}
+
+static bool small_m_ok(const ConvParams& p) {
+  return p.M <= 1024 && p.KT == 1 && p.KF == 1 && p.sT == 1 && p.sF == 1 && p.padT == 0 && p.padF == 0 &&
+         p.src2_mode == VP_SRC2_NONE && p.pre_s == nullptr && p.Tin == p.Tout && p.Fin == p.Fout && (p.K & 3) == 0;
+}
+
 cudaError_t launch_conv_ffma(const ConvParams& p, cudaStream_t stream) {
   dim3 block(256);
+  if (small_m_ok(p)) {
+    dim3 grid((p.N + 31) / 32, (p.M + 7) / 8);
+    linear_small_m_kernel<<<grid, block, 0, stream>>>(p);
+    return cudaGetLastError();
+  }
   if (p.N > 64) {
     dim3 grid((p.M + BM - 1) / BM, (p.N + 127) / 128);
     conv_ffma_kernel<128><<<grid, block, 0, stream>>>(p);

@@ -6,18 +6,20 @@
 // so every operand is split  x = hi + lo,  hi = tf32(x),  lo = x - hi  and three MMAs are accumulated in fp32 TMEM:
 //   D += A_lo * B_hi;  D += A_hi * B_lo;  D += A_hi * B_hi        (the dropped lo*lo term is ~2^-22 relative).
 //
-// Persistent, warp-specialised CTA (320 threads), one CTA per SM:
+// Persistent, warp-specialised CTA (448 threads), one CTA per SM:
 //   warps 0-3  epilogue   : tcgen05.ld accumulator rows from TMEM -> fused epilogue (bias / ubias / act / BN affine /
 //                           gate / residual / act2) -> float4 stores; TMEM accumulators are double buffered so the
 //                           epilogue of tile i overlaps the MMAs of tile i+1
-//   warps 4-7  A producers: gather the implicit-GEMM A tile straight from the channel-last activation map (any tap /
+//   warps 4-11 A producers: gather the implicit-GEMM A tile straight from the channel-last activation map (any tap /
 //                           dilation / stride / reflect or zero padding / add or concat second source / BN-ReLU
 //                           prologue: common.cuh::gather_a4) with coalesced 128 B row segments, split into hi / lo and
 //                           write both in the UMMA K-major SWIZZLE_128B shared-memory layout
-//   warp 8     B loader   : weights are pre-split and pre-tiled on the host in exactly that shared-memory image, so one
+//   warp 12    B loader   : weights are pre-split and pre-tiled on the host in exactly that shared-memory image, so one
 //                           bulk-async copy (TMA engine, cp.async.bulk -> UBLKCP) per stage lands B_hi|B_lo
-//   warp 9     MMA issuer : one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8), commits to mbarriers
+//   warp 13    MMA issuer : one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8), commits to mbarriers
 // Pipeline: S shared-memory stages (full/empty mbarriers) + 2 TMEM accumulator buffers (tmem_full/tmem_empty).
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace vpb {
@@ -27,9 +29,12 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 32;                  // fp32 elements per stage row = 128 B = one SWIZZLE_128B row
 constexpr int A_TILE = BM * BK * 4;     // 16 KB per (hi|lo) A tile
-constexpr int NUM_THREADS = 320;
-constexpr int PRODUCER_THREADS = 128;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int PRODUCER_WARPS = 8;
+constexpr int PRODUCER_THREADS = PRODUCER_WARPS * 32;      // 256
+constexpr int NUM_THREADS = 128 + PRODUCER_THREADS + 64;   // 4 epilogue + 8 producer + loader + MMA warps
+constexpr int ROWS_PER_THREAD = BM * 8 / PRODUCER_THREADS;   // 4
+constexpr int SMEM_BUDGET = 200 * 1024;            // pipeline stages
+constexpr int EPI_PAD_BYTES = 4 * 32 * 36 * 4;       // 4 epilogue warps x (32 rows x 36 floats) transpose pads
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -57,6 +62,20 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void bulk_copy_g2s_mcast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -122,11 +141,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   const int S = a.stages;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]);
   const uint32_t tfull0 = smem_u32(&bars[16]), tempty0 = smem_u32(&bars[18]);
+  // Thread-block cluster of C CTAs working on C consecutive M tiles of the SAME N tile: every CTA fetches 1/C of each B
+  // stage and multicasts it to all C shared memories (L2 -> SM weight traffic / C); a stage is recycled only when the
+  // MMAs of all C CTAs have consumed it (multicast tcgen05.commit on every CTA's `empty` barrier).
+  const uint32_t C = cluster_nctarank();
+  const uint32_t crank = cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << C) - 1u);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full0 + 8 * s, PRODUCER_THREADS + 1);          // 128 A-producer arrivals + 1 expect_tx arrival (B)
-      mbar_init(empty0 + 8 * s, 1);                            // one tcgen05.commit
+      mbar_init(empty0 + 8 * s, C);                            // one tcgen05.commit from every CTA of the cluster
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull0 + 8 * i, 1);
@@ -142,25 +167,75 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
+  if (C > 1) cluster_sync_all();           // peers' mbarriers are initialised before any remote arrive / multicast lands
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  const int total_tiles = a.m_tiles * a.n_tiles;
+  // work distribution: group g = (m_group, n_tile); CTA `crank` of the cluster takes M tile m_group*C + crank
+  const int n_clusters = gridDim.x / C, cluster_id = blockIdx.x / C;
+  const int m_groups = (a.m_tiles + C - 1) / C;
+  const int total_groups = m_groups * a.n_tiles;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 4 && warp < 4 + PRODUCER_WARPS) {
     // =========================== A producers ===========================
-    const int t = threadIdx.x - 128;       // 0..127
-    const int chunk = t & 7;               // 16-byte chunk inside the 128-byte K row
-    const int r0 = t >> 3;                 // rows r0 + 16*i
+    // Thread t owns the 16-byte chunk `chunk` of rows r0 + 32*i: a warp-level load covers 4 rows x 128 contiguous bytes.
+    // All tap / channel arithmetic is per K block (uniform over the thread's rows); per row only the bounds test remains.
+    const int t = threadIdx.x - 128;
+    const int chunk = t & 7;
+    const int r0 = t >> 3;                 // 0..31
+    const bool pointwise = (p.KT * p.KF == 1);
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (tile / a.n_tiles) * BM;
-      RowInfo rows[8];
+    for (int g = cluster_id; g < total_groups; g += n_clusters) {
+      const int m0 = ((g / a.n_tiles) * (int)C + (int)crank) * BM;
+      RowInfo rows[ROWS_PER_THREAD];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) rows[i] = decode_row(p, m0 + r0 + 16 * i);
-      float4 v[8];
+      for (int i = 0; i < ROWS_PER_THREAD; ++i) rows[i] = decode_row(p, m0 + r0 + 32 * i);
+      float4 v[ROWS_PER_THREAD];
+      auto gather = [&](int kb) {
+        const int k = kb * BK + chunk * 4;
+        int ci = k, dt = 0, df = 0;
+        if (!pointwise) {
+          const int tap = k / p.CinTot;
+          ci = k - tap * p.CinTot;
+          const int kt = tap / p.KF;
+          dt = kt * p.dT;
+          df = (tap - kt * p.KF) * p.dF;
+        }
+        const bool kok = k < p.K;
+        const bool second = (p.src2_mode == VP_SRC2_CONCAT) && (ci >= p.Cin);
+        const float* base = second ? p.src2 + p.src2_coff + (ci - p.Cin) : p.src + p.in_coff + ci;
+        const int ld = second ? p.src2_ld : p.in_ld;
+        float4 ps = make_float4(1.f, 1.f, 1.f, 1.f), ph = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.pre_s != nullptr && kok) {
+          ps = __ldg(reinterpret_cast<const float4*>(p.pre_s + ci));
+          ph = __ldg(reinterpret_cast<const float4*>(p.pre_h + ci));
+        }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = gather_a4(p, rows[i], chunk * 4);
+        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+          int ti = rows[i].t0 + dt;
+          const int fi = rows[i].f0 + df;
+          if (p.pad_mode == VP_PAD_REFLECT) {
+            if (ti < 0) ti = -ti;
+            if (ti >= p.Tin) ti = 2 * (p.Tin - 1) - ti;
+          }
+          const bool ok = kok && rows[i].valid && ti >= 0 && ti < p.Tin && fi >= 0 && fi < p.Fin;
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) {
+            const size_t row = (size_t)rows[i].base + (size_t)ti * p.Fin + fi;
+            x = __ldg(reinterpret_cast<const float4*>(base + row * ld));
+            if (p.src2_mode == VP_SRC2_ADD) {
+              const float4 u = __ldg(reinterpret_cast<const float4*>(p.src2 + row * p.src2_ld + p.src2_coff + ci));
+              x.x += u.x; x.y += u.y; x.z += u.z; x.w += u.w;
+            }
+            if (p.pre_s != nullptr) {
+              x.x = fmaf(x.x, ps.x, ph.x); x.y = fmaf(x.y, ps.y, ph.y); x.z = fmaf(x.z, ps.z, ph.z); x.w = fmaf(x.w, ps.w, ph.w);
+              if (p.pre_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            }
+          }
+          v[i] = x;
+        }
+      };
+      gather(0);
       for (int kb = 0; kb < a.k_blocks; ++kb, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
@@ -168,8 +243,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const uint32_t a_hi = smem_base + s * stage_bytes;
         const uint32_t a_lo = a_hi + A_TILE;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + 16 * i;
+        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+          const int r = r0 + 32 * i;
           const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
           float4 hi, lo;
           hi.x = tf32_rna(v[i].x); hi.y = tf32_rna(v[i].y); hi.z = tf32_rna(v[i].z); hi.w = tf32_rna(v[i].w);
@@ -179,36 +254,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
         mbar_arrive(full0 + 8 * s);
-        if (kb + 1 < a.k_blocks) {           // prefetch the next K block into registers while this one is consumed
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = gather_a4(p, rows[i], (kb + 1) * BK + chunk * 4);
-        }
+        if (kb + 1 < a.k_blocks) gather(kb + 1);   // next K block's loads fly while this one is multiplied
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 4 + PRODUCER_WARPS) {
     // =========================== B loader (bulk async copy) ===========================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % a.n_tiles;
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.w_tc) + (size_t)nt * a.k_blocks * (2u * b_tile);
+      const uint32_t slice = 2u * b_tile / C;                 // this CTA's share of every B stage
+      for (int g = cluster_id; g < total_groups; g += n_clusters) {
+        const int nt = g % a.n_tiles;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.w_tc) + (size_t)nt * a.k_blocks * (2u * b_tile) + crank * slice;
         for (int kb = 0; kb < a.k_blocks; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(empty0 + 8 * s, ph ^ 1);
-          mbar_expect_tx(full0 + 8 * s, 2u * b_tile);
-          bulk_copy_g2s(smem_base + s * stage_bytes + 2u * A_TILE, src + (size_t)kb * (2u * b_tile), 2u * b_tile,
-                        full0 + 8 * s);
+          mbar_expect_tx(full0 + 8 * s, 2u * b_tile);          // the whole stage lands here (own slice + peers' multicasts)
+          const uint32_t dst = smem_base + s * stage_bytes + 2u * A_TILE + crank * slice;
+          if (C > 1) bulk_copy_g2s_mcast(dst, src + (size_t)kb * (2u * b_tile), slice, full0 + 8 * s, cmask);
+          else bulk_copy_g2s(dst, src + (size_t)kb * (2u * b_tile), slice, full0 + 8 * s);
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 5 + PRODUCER_WARPS) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       // kind::tf32 instruction descriptor: D=F32 (bit 4), A=B=TF32 (2 at bits 7 and 10), K-major, N>>3 @17, M>>4 @24
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      for (int g = cluster_id; g < total_groups; g += n_clusters, ++tcount) {
         const int acc = tcount & 1;
         mbar_wait(tempty0 + 8 * acc, ((tcount >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -227,52 +301,93 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             umma_tf32(d, dah, dbl, idesc, 1);
             umma_tf32(d, dah, dbh, idesc, 1);
           }
-          umma_commit(empty0 + 8 * s);                        // frees the smem stage when these MMAs retire
+          if (C > 1) umma_commit_mcast(empty0 + 8 * s, cmask);   // frees the stage in every CTA of the cluster
+          else umma_commit(empty0 + 8 * s);                   // frees the smem stage when these MMAs retire
         }
         umma_commit(tfull0 + 8 * acc);                        // accumulator ready for the epilogue
       }
     }
   } else {
     // =========================== epilogue (warps 0-3 <-> TMEM lanes 32*warp ..) ===========================
+    // Per 32-column chunk: tcgen05.ld gives each thread (= accumulator row) 32 consecutive columns; the chunk is
+    // transposed through a private 32 x 36-float shared-memory pad so that the fused epilogue and the global stores run
+    // with lanes along N: every store/residual instruction covers 4 rows x 128 contiguous bytes, and the per-column
+    // parameters are one float4 per chunk.
+    float* pad = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)S * stage_bytes) + warp * (32 * 36);
+    const uint32_t pad_u32 = smem_base + S * stage_bytes + warp * (32 * 36 * 4);
+    const int cg = (lane & 7) * 4;           // this thread's 4 columns inside the chunk
+    const int rsub = lane >> 3;              // rows rsub + 4*i
+    const bool need_urow = (p.gate != nullptr) || (p.ubias != nullptr);
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    for (int g = cluster_id; g < total_groups; g += n_clusters, ++tcount) {
       const int acc = tcount & 1;
-      const int m = (tile / a.n_tiles) * BM + warp * 32 + lane;
-      const int n0 = (tile % a.n_tiles) * BN;
+      const int mbase = ((g / a.n_tiles) * (int)C + (int)crank) * BM + warp * 32;
+      const int n0 = (g % a.n_tiles) * BN;
+      int urow[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = mbase + rsub + 4 * i;
+        urow[i] = (need_urow && m < p.M) ? urow_of(p, m) : 0;
+      }
       mbar_wait(tfull0 + 8 * acc, (tcount >> 1) & 1);
       tc_fence_after();
-      const bool mok = m < p.M;
-      const int urow = mok ? urow_of(p, m) : 0;
-      float* orow = p.dst + (size_t)(mok ? m : 0) * p.out_ld + p.out_coff;
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), v);
-        if (mok) {
+        {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+          if (c0 + 32 >= BN) {                // last read of this accumulator buffer: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(tempty0 + 8 * acc);
+          }
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int n = n0 + c0 + j;
-            if (n + 3 < p.N) {
-              float4 o;
-              o.x = epilogue1(p, v[j + 0], m, n + 0, urow);
-              o.y = epilogue1(p, v[j + 1], m, n + 1, urow);
-              o.z = epilogue1(p, v[j + 2], m, n + 2, urow);
-              o.w = epilogue1(p, v[j + 3], m, n + 3, urow);
-              *reinterpret_cast<float4*>(orow + n) = o;
-            } else {
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pad_u32 + (uint32_t)(lane * 36 + j) * 4u), "f"(v[j]),
+                         "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
+                         : "memory");
+        }
+        __syncwarp();
+        const int n = n0 + c0 + cg;
+        if (n < p.N) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = b4;
+          if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          if (p.post_s) {
+            s4 = __ldg(reinterpret_cast<const float4*>(p.post_s + n));
+            h4 = __ldg(reinterpret_cast<const float4*>(p.post_h + n));
+          }
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (n + q < p.N) orow[n + q] = epilogue1(p, v[j + q], m, n + q, urow);
+          for (int i = 0; i < 8; ++i) {
+            const int row = rsub + 4 * i;
+            const int m = mbase + row;
+            if (m < p.M) {
+              float4 v = *reinterpret_cast<const float4*>(pad + row * 36 + cg);
+              v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+              if (p.ubias) {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(p.ubias + (size_t)urow[i] * p.N + n));
+                v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+              }
+              if (p.act) { v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act); }
+              if (p.post_s) { v.x = fmaf(v.x, s4.x, h4.x); v.y = fmaf(v.y, s4.y, h4.y); v.z = fmaf(v.z, s4.z, h4.z); v.w = fmaf(v.w, s4.w, h4.w); }
+              if (p.gate) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)urow[i] * p.N + n));
+                v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+              }
+              if (p.res) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(p.res + (size_t)m * p.res_ld + p.res_coff + n));
+                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+              }
+              if (p.act2) { v.x = apply_act(v.x, p.act2); v.y = apply_act(v.y, p.act2); v.z = apply_act(v.z, p.act2); v.w = apply_act(v.w, p.act2); }
+              *reinterpret_cast<float4*>(p.dst + (size_t)m * p.out_ld + p.out_coff + n) = v;
             }
           }
         }
+        __syncwarp();
       }
-      tc_fence_before();
-      mbar_arrive(tempty0 + 8 * acc);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (C > 1) cluster_sync_all();           // no CTA exits while a peer may still multicast into it
   if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols) : "memory");
@@ -310,19 +425,41 @@ cudaError_t launch_conv_tc(const ConvParams& p, cudaStream_t stream) {
   a.m_tiles = (p.M + BM - 1) / BM;
   a.n_tiles = (p.N + a.BN - 1) / a.BN;
   a.k_blocks = (p.K + BK - 1) / BK;
-  const size_t smem = (size_t)a.stages * stage_bytes + 1024;
+  const size_t smem = (size_t)a.stages * stage_bytes + EPI_PAD_BYTES + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int tiles = a.m_tiles * a.n_tiles;
-  const int grid = tiles < sms ? tiles : sms;
-  conv_tc_kernel<<<grid, NUM_THREADS, smem, stream>>>(p, a);
+  static int cluster_pref = -1;
+  if (cluster_pref < 0) {
+    const char* e = getenv("VPB_TC_CLUSTER");
+    cluster_pref = e ? atoi(e) : 2;
+    if (cluster_pref != 1 && cluster_pref != 2 && cluster_pref != 4) cluster_pref = 2;
+  }
+  int C = cluster_pref;
+  while (C > 1 && (a.m_tiles < 2 * C || ((2 * a.BN * 128 / C) & 15))) C >>= 1;
+  const int groups = ((a.m_tiles + C - 1) / C) * a.n_tiles;
+  int clusters = sms / C;
+  if (clusters > groups) clusters = groups;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * C);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel, p, a);
+  if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }
 
