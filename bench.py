@@ -257,6 +257,12 @@ def run_gpu_arm(args):
     clocks = ClockSampler(local) if rank == 0 else None
     ms_res = timed(step_resident, args.steps, args.warmup)
     clk = clocks.stop() if clocks else None
+    if args.light:
+        if rank == 0:
+            print(json.dumps({'light': True, 'ms_per_step': ms_res / args.steps, 'note': 'not a bench value'}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
 
     # sanity inside the bench: the embeddings of the last step agree with the CPU oracle on 2 utterances
@@ -350,6 +356,8 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--light', action='store_true', help='resident-input timing only (for runs under ncu): no e2e / '
+                    'cpu baseline / per-op profile; the JSON line is NOT a bench value')
     ap.add_argument('--dump-ops', default=None, help='write the per-op device-time profile (JSON) to this path')
     args = ap.parse_args()
     if args.impl == 'reference':
