@@ -14,7 +14,7 @@ class AudioSegment:
         s = np.asarray(samples)
         if s.dtype.kind in 'iu':
             s = s.astype(np.float32) / float(2 ** (8 * s.dtype.itemsize - 1))
-        s = s.astype(np.float32)
+        s = s.astype(np.float32, copy=False)
         if s.ndim == 2:                       # [n, channels] -> mono
             s = s.mean(axis=1)
         self.samples = s

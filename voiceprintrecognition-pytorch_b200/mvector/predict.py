@@ -57,6 +57,7 @@ class MVectorPredictor:
         logger.info(f"成功加载模型参数：{model_path}")
         self.predictor.eval()
         self._pinned = None
+        self._copy_stream = None
 
         self.audio_feature = None
         self.audio_feature_mean = None
@@ -171,56 +172,86 @@ class MVectorPredictor:
             audio_segment.normalize(target_db=ds.target_dB)
         return audio_segment
 
-    def _pinned_batch(self, B, Lp):
-        """Reusable pinned host staging buffer viewed as [B, Lp] float32."""
-        n = B * Lp
-        if self._pinned is None or self._pinned.numel() < n:
-            self._pinned = torch.empty(max(n, 1 << 20), dtype=torch.float32).pin_memory()
-        return self._pinned[:n].view(B, Lp)
+    #: utterances per pipeline chunk of predict_batch (host gather + H2D of chunk k+1 overlap the kernels of chunk k)
+    CHUNK = 64
 
-    def _embed_host(self, host, lens_ratio):
-        """host: pinned float32 [B, Lmax] (zero padded) -> np.float32 [B, embd_dim].  One H2D, ONE fused C-ABI call
-        (vp_embed_wave: front-end + CMN/mask + backbone), one D2H."""
+    def _pinned_slot(self, slot, n):
+        """Two reusable pinned host staging buffers (double buffering)."""
+        if self._pinned is None:
+            self._pinned = [None, None]
+        if self._pinned[slot] is None or self._pinned[slot].numel() < n:
+            self._pinned[slot] = torch.empty(max(n, 1 << 20), dtype=torch.float32).pin_memory()
+        return self._pinned[slot][:n]
+
+    def _embed_waves(self, waves, lmax, masked):
+        """waves: list of 1-D float32 arrays (already loaded / resampled / normalised) -> np.float32 [B, embd_dim].
+
+        Reference semantics (predict.py:244-262): every utterance is zero padded to the longest item of the WHOLE list,
+        T and the CMN mean follow that padded length, frames >= round(len/Lmax * T) are zeroed.  Because every op is
+        per-utterance, the list is processed in chunks of CHUNK utterances: while the GPU runs the fused
+        ``vp_embed_wave`` of chunk k, the host gathers chunk k+1 into pinned memory and its H2D copy runs on a second
+        stream.  One D2H of the [B, embd] result at the end."""
         from . import _lib as L
-        B, Lp = host.shape
-        wave = host.to(self.device, non_blocking=True)
+        B = len(waves)
         fz = self._audio_featurizer
-        T = fz.num_frames(Lp)
+        T = fz.num_frames(lmax)
         if fz.feat_fun.desc.kind == 0:
-            assert 2 <= fz.feat_fun.win_length <= Lp, f'choose a window size {fz.feat_fun.win_length} that is [2, {Lp}]'
-        keep = None
-        if lens_ratio is not None:
-            keep = fz.keep_frames(lens_ratio, T).to(self.device, non_blocking=True)
-        prog = self.predictor.program(B, T)
+            assert 2 <= fz.feat_fun.win_length <= lmax, f'choose a window size {fz.feat_fun.win_length} that is [2, {lmax}]'
+        dev = self.device
+        keep_all = None
+        if masked:
+            keep_all = fz.keep_frames(torch.tensor([w.shape[0] / lmax for w in waves], dtype=torch.float32), T).to(dev)
         eng = fz.engine
-        feats = torch.empty(B * T * fz.feat_fun.n_mels, dtype=torch.float32, device=self.device)
-        scratch = torch.empty(max(int(L.lib().vp_frontend_scratch_floats(eng.handle, B, Lp)), 1), dtype=torch.float32,
-                              device=self.device)
-        emb = torch.empty(B, self.predictor.embd_dim, dtype=torch.float32, device=self.device)
-        prog.run_wave(wave, keep, feats, scratch, emb)
+        F = fz.feat_fun.n_mels
+        D = self.predictor.embd_dim
+        emb = torch.empty(B, D, dtype=torch.float32, device=dev)
+        cb = min(self.CHUNK, B)
+        feats = torch.empty(cb * T * F, dtype=torch.float32, device=dev)
+        scratch = torch.empty(max(int(L.lib().vp_frontend_scratch_floats(eng.handle, cb, lmax)), 1), dtype=torch.float32,
+                              device=dev)
+        dwave = [torch.empty(cb * lmax, dtype=torch.float32, device=dev) for _ in range(2)]
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        free_ev = [None, None]                       # compute finished reading device/pinned slot
+        for ci, lo in enumerate(range(0, B, cb)):
+            hi = min(lo + cb, B)
+            n = hi - lo
+            slot = ci & 1
+            if free_ev[slot] is not None:
+                free_ev[slot].synchronize()          # pinned slot may be overwritten only after its H2D + kernels
+            host = self._pinned_slot(slot, n * lmax).view(n, lmax)
+            hnp = host.numpy()
+            for i in range(n):                       # zero padding to the global longest item (predict.py:248-254)
+                w = waves[lo + i]
+                m = w.shape[0]
+                hnp[i, :m] = w
+                if m < lmax:
+                    hnp[i, m:] = 0.0
+            dw = dwave[slot][:n * lmax].view(n, lmax)
+            with torch.cuda.stream(self._copy_stream):
+                dw.copy_(host, non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(self._copy_stream)
+            main.wait_event(copied)
+            keep = keep_all[lo:hi] if keep_all is not None else None
+            self.predictor.program(n, T).run_wave(dw, keep, feats, scratch, emb[lo:hi])
+            done = torch.cuda.Event()
+            done.record(main)
+            free_ev[slot] = done                     # slot (pinned + device) reusable once these kernels finished
         return emb.cpu().numpy()
 
     def predict(self, audio_data, sample_rate=16000):
         """预测一个音频的特征 (predict.py:214-229) -> np.ndarray [embd_dim]"""
         seg = self._load_audio(audio_data=audio_data, sample_rate=sample_rate)
-        host = self._pinned_batch(1, seg.samples.shape[0])
-        host[0].copy_(torch.from_numpy(np.ascontiguousarray(seg.samples, dtype=np.float32)))
-        return self._embed_host(host, None)[0]
+        w = np.ascontiguousarray(seg.samples, dtype=np.float32)
+        return self._embed_waves([w], w.shape[0], masked=False)[0]
 
     def predict_batch(self, audios_data, sample_rate=16000, batch_size=32):
         """预测一批音频的特征 (predict.py:231-265) -> np.ndarray [B, embd_dim], order preserved."""
         waves = [self._load_audio(audio_data=a, sample_rate=sample_rate).samples for a in audios_data]
         lmax = max(w.shape[0] for w in waves)
-        host = self._pinned_batch(len(waves), lmax)
-        hnp = host.numpy()
-        ratio = []
-        for i, w in enumerate(waves):                     # zero padding to the longest item (predict.py:248-254)
-            n = w.shape[0]
-            hnp[i, :n] = w
-            if n < lmax:
-                hnp[i, n:] = 0.0
-            ratio.append(n / lmax)
-        return self._embed_host(host, torch.tensor(ratio, dtype=torch.float32))
+        return self._embed_waves(waves, lmax, masked=True)
 
     def contrast(self, audio_data1, audio_data2):
         """声纹对比 (predict.py:267-279) -> cosine similarity"""
