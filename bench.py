@@ -283,6 +283,11 @@ def run_gpu_arm(args):
     ms_res = timed(step_resident, args.steps, args.warmup)
     clk = clocks.stop() if clocks else None
     mark(f'resident timing done: {ms_res:.2f} ms')
+    if os.environ.get('VPB_E2E_ONLY'):
+        ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+        if rank == 0:
+            print(json.dumps({'e2e_only': True, 'ms_per_step': ms_e2e / args.steps, 'emb_per_s': B * world * args.steps / (ms_e2e * 1e-3)}))
+        return
     if args.light:
         if rank == 0:
             print(json.dumps({'light': True, 'ms_per_step': ms_res / args.steps, 'note': 'not a bench value'}))

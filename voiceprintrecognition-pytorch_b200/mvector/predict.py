@@ -58,6 +58,7 @@ class MVectorPredictor:
         self.predictor.eval()
         self._pinned = None
         self._copy_stream = None
+        self._pool = None
 
         self.audio_feature = None
         self.audio_feature_mean = None
@@ -173,7 +174,8 @@ class MVectorPredictor:
         return audio_segment
 
     #: utterances per pipeline chunk of predict_batch (host gather + H2D of chunk k+1 overlap the kernels of chunk k)
-    CHUNK = 64
+    CHUNK = int(os.environ.get('VPB_PREDICT_CHUNK', '128'))
+    GATHER_THREADS = 4
 
     def _pinned_slot(self, slot, n):
         """Two reusable pinned host staging buffers (double buffering)."""
@@ -222,12 +224,21 @@ class MVectorPredictor:
                 free_ev[slot].synchronize()          # pinned slot may be overwritten only after its H2D + kernels
             host = self._pinned_slot(slot, n * lmax).view(n, lmax)
             hnp = host.numpy()
-            for i in range(n):                       # zero padding to the global longest item (predict.py:248-254)
-                w = waves[lo + i]
-                m = w.shape[0]
-                hnp[i, :m] = w
-                if m < lmax:
-                    hnp[i, m:] = 0.0
+            def fill(r0, r1, hnp=hnp, lo=lo):          # zero padding to the global longest item (predict.py:248-254)
+                for i in range(r0, r1):
+                    w = waves[lo + i]
+                    m = w.shape[0]
+                    hnp[i, :m] = w
+                    if m < lmax:
+                        hnp[i, m:] = 0.0
+            if n >= 32 and self.GATHER_THREADS > 1:   # numpy releases the GIL while copying: gather with a few threads
+                if self._pool is None:
+                    from concurrent.futures import ThreadPoolExecutor
+                    self._pool = ThreadPoolExecutor(max_workers=self.GATHER_THREADS)
+                step = -(-n // self.GATHER_THREADS)
+                list(self._pool.map(lambda r: fill(r, min(r + step, n)), range(0, n, step)))
+            else:
+                fill(0, n)
             dw = dwave[slot][:n * lmax].view(n, lmax)
             with torch.cuda.stream(self._copy_stream):
                 dw.copy_(host, non_blocking=True)
