@@ -147,28 +147,40 @@ __global__ void __launch_bounds__(256, 2) conv_ffma_kernel(const __grid_constant
 // each weight row, then a fixed-order butterfly reduction -> deterministic.  grid = (ceil(N/32), ceil(M/8)).
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) linear_small_m_kernel(const __grid_constant__ ConvParams p) {
+  // W tile [32 output columns][128 K] staged in shared memory once per CTA and K chunk, shared by the CTA's 8 rows
+  __shared__ __align__(16) float ws[32][132];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int m = blockIdx.y * 8 + wid;
   const int n0 = blockIdx.x * 32;
-  if (m >= p.M) return;
-  const float* x = p.src + (size_t)m * p.in_ld + p.in_coff;      // pointwise, stride 1: source row == output row
+  const bool mok = m < p.M;
+  const float* x = p.src + (size_t)(mok ? m : 0) * p.in_ld + p.in_coff;   // pointwise, stride 1: source row == output row
   float acc[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-  for (int k = lane * 4; k < p.K; k += 128) {
-    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + k));
+  for (int k0 = 0; k0 < p.K; k0 += 128) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                       // 32 rows x 32 float4 = 1024 float4, 4 per thread, coalesced rows
+      const int idx = threadIdx.x + i * 256;
+      const int j = idx >> 5, c = (idx & 31) * 4;
+      float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + j < p.N && k0 + c < p.K) wv = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)(n0 + j) * p.w_ld + k0 + c));
+      *reinterpret_cast<float4*>(&ws[j][c]) = wv;
+    }
+    __syncthreads();
+    const int k = k0 + lane * 4;
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mok && k < p.K) xv = __ldg(reinterpret_cast<const float4*>(x + k));
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      if (n0 + j < p.N) {
-        const float4 wv = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)(n0 + j) * p.w_ld + k));
-        acc[j] = fmaf(xv.x, wv.x, acc[j]);
-        acc[j] = fmaf(xv.y, wv.y, acc[j]);
-        acc[j] = fmaf(xv.z, wv.z, acc[j]);
-        acc[j] = fmaf(xv.w, wv.w, acc[j]);
-      }
+      const float4 wv = *reinterpret_cast<const float4*>(&ws[j][lane * 4]);
+      acc[j] = fmaf(xv.x, wv.x, acc[j]);
+      acc[j] = fmaf(xv.y, wv.y, acc[j]);
+      acc[j] = fmaf(xv.z, wv.z, acc[j]);
+      acc[j] = fmaf(xv.w, wv.w, acc[j]);
     }
   }
-  // transpose-reduce: after the butterfly lane j holds the total of column j
+  // transpose-reduce: after the butterfly lane j holds the total of column j (fixed order -> deterministic)
   float mine = 0.f;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
@@ -176,7 +188,7 @@ __global__ void __launch_bounds__(256) linear_small_m_kernel(const __grid_consta
     if (lane == j) mine = t;
   }
   const int n = n0 + lane;
-  if (n < p.N) p.dst[(size_t)m * p.out_ld + p.out_coff + n] = epilogue1(p, mine, m, n, urow_of(p, m));
+  if (mok && n < p.N) p.dst[(size_t)m * p.out_ld + p.out_coff + n] = epilogue1(p, mine, m, n, urow_of(p, m));
 }
 
 static bool small_m_ok(const ConvParams& p) {

@@ -190,8 +190,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       RowInfo rows[ROWS_PER_THREAD];
 #pragma unroll
       for (int i = 0; i < ROWS_PER_THREAD; ++i) rows[i] = decode_row(p, m0 + r0 + 32 * i);
-      float4 v[ROWS_PER_THREAD];
-      auto gather = [&](int kb) {
+      float4 v0[ROWS_PER_THREAD], v1[ROWS_PER_THREAD], v2[ROWS_PER_THREAD];   // 3 K blocks of loads in flight
+      auto gather = [&](int kb, float4 (&v)[ROWS_PER_THREAD]) {
         const int k = kb * BK + chunk * 4;
         int ci = k, dt = 0, df = 0;
         if (!pointwise) {
@@ -235,10 +235,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           v[i] = x;
         }
       };
-      gather(0);
-      for (int kb = 0; kb < a.k_blocks; ++kb, ++it) {
+      auto publish = [&](int kb, float4 (&v)[ROWS_PER_THREAD]) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
+        ++it;
         mbar_wait(empty0 + 8 * s, ph ^ 1);
         const uint32_t a_hi = smem_base + s * stage_bytes;
         const uint32_t a_lo = a_hi + A_TILE;
@@ -254,7 +254,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
         mbar_arrive(full0 + 8 * s);
-        if (kb + 1 < a.k_blocks) gather(kb + 1);   // next K block's loads fly while this one is multiplied
+        if (kb + 3 < a.k_blocks) gather(kb + 3, v);   // refill this register slot: 3 K blocks of loads stay in flight
+      };
+      gather(0, v0);
+      if (a.k_blocks > 1) gather(1, v1);
+      if (a.k_blocks > 2) gather(2, v2);
+      for (int kb = 0; kb < a.k_blocks; kb += 3) {
+        publish(kb, v0);
+        if (kb + 1 < a.k_blocks) publish(kb + 1, v1);
+        if (kb + 2 < a.k_blocks) publish(kb + 2, v2);
       }
     }
   } else if (warp == 4 + PRODUCER_WARPS) {

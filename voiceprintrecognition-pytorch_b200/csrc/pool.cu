@@ -135,8 +135,78 @@ __global__ void __launch_bounds__(256) asp_pool_kernel(const __grid_constant__ A
   }
 }
 
+// Same computation with the [T, 32-column] strips of x and logits staged ONCE in shared memory (each read from HBM once,
+// coalesced 128 B rows), then the three softmax / mean / variance sweeps run out of shared memory.
+__global__ void __launch_bounds__(256) asp_pool_smem_kernel(const __grid_constant__ AspParams p) {
+  extern __shared__ float sm[];
+  __shared__ float red[8][33];
+  __shared__ float bc[32];
+  float* sx = sm;                       // [T][32]
+  float* sl = sm + (size_t)p.T * 32;    // [T][32]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int b = blockIdx.y;
+  const bool ok = c < p.C;
+  const float* x = p.x + (size_t)b * p.T * p.x_ld + p.x_coff + c;
+  const float* l = p.logit + (size_t)b * p.T * p.l_ld + p.l_coff + c;
+  for (int t = wid; t < p.T; t += 8) {
+    sx[t * 32 + lane] = ok ? __ldg(x + (size_t)t * p.x_ld) : 0.f;
+    sl[t * 32 + lane] = ok ? __ldg(l + (size_t)t * p.l_ld) : 0.f;
+  }
+  __syncthreads();
+  auto block_reduce = [&](float v, bool is_max) -> float {
+    red[wid][lane] = v;
+    __syncthreads();
+    if (wid == 0) {
+      float s = red[0][lane];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) s = is_max ? fmaxf(s, red[i][lane]) : s + red[i][lane];
+      bc[lane] = s;
+    }
+    __syncthreads();
+    float r = bc[lane];
+    __syncthreads();
+    return r;
+  };
+  float mx = -INFINITY;
+  for (int t = wid; t < p.T; t += 8) mx = fmaxf(mx, sl[t * 32 + lane]);
+  mx = block_reduce(mx, true);
+  float se = 0.f, sxe = 0.f;
+  for (int t = wid; t < p.T; t += 8) {
+    const float e = expf(sl[t * 32 + lane] - mx);
+    sl[t * 32 + lane] = e;                              // keep exp() for the variance sweep
+    se += e;
+    sxe = fmaf(e, sx[t * 32 + lane], sxe);
+  }
+  se = block_reduce(se, false);
+  sxe = block_reduce(sxe, false);
+  const float mean = sxe / se;
+  float sq = 0.f;
+  for (int t = wid; t < p.T; t += 8) {
+    const float d = sx[t * 32 + lane] - mean;
+    sq = fmaf(sl[t * 32 + lane], d * d, sq);
+  }
+  sq = block_reduce(sq, false);
+  if (wid == 0 && ok) {
+    float* o = p.dst + (size_t)b * p.out_ld + p.out_coff;
+    o[c] = mean;
+    o[p.C + c] = sqrtf(fmaxf(sq / se, p.eps));
+  }
+}
+
 cudaError_t launch_asp_pool(const AspParams& p, cudaStream_t stream) {
   dim3 grid((p.C + 31) / 32, p.B);
+  const size_t smem = (size_t)p.T * 32 * 2 * sizeof(float);
+  if (smem <= 200 * 1024) {
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(asp_pool_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return e;
+      configured = 200 * 1024;
+    }
+    asp_pool_smem_kernel<<<grid, 256, smem, stream>>>(p);
+    return cudaGetLastError();
+  }
   asp_pool_kernel<<<grid, 256, 0, stream>>>(p);
   return cudaGetLastError();
 }
