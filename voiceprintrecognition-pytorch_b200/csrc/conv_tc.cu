@@ -118,14 +118,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+template <int MODE> struct Slot;
+template <> struct Slot<0> { float4 v[ROWS_PER_THREAD]; };
+template <> struct Slot<1> { float4 v[ROWS_PER_THREAD]; float4 u[ROWS_PER_THREAD]; };
+template <> struct Slot<2> { float4 v[ROWS_PER_THREAD]; float4 ps, ph; uint32_t okmask; };
+
 struct TcArgs {
   const float* w_tc;     // pre-split, pre-tiled, pre-swizzled weights: [n_tile][k_block][hi BN x 128 B | lo BN x 128 B]
   int BN;                // N tile (multiple of 16, <= 256)
   int stages;
   int tmem_cols;         // power of two >= 2*BN
   int m_tiles, n_tiles, k_blocks;
+  int debug;             // experiments only (VPB_TC_DEBUG): 1 = skip B copies, 2 = skip A global loads, 4 = skip MMAs
 };
 
+template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p,
                                                                  const __grid_constant__ TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full0 + 8 * s, PRODUCER_THREADS + 1);          // 128 A-producer arrivals + 1 expect_tx arrival (B)
+      mbar_init(full0 + 8 * s, PRODUCER_WARPS + 1);            // one arrival per A-producer warp + 1 expect_tx arrival (B)
       mbar_init(empty0 + 8 * s, C);                            // one tcgen05.commit from every CTA of the cluster
     }
     for (int i = 0; i < 2; ++i) {
@@ -190,8 +197,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       RowInfo rows[ROWS_PER_THREAD];
 #pragma unroll
       for (int i = 0; i < ROWS_PER_THREAD; ++i) rows[i] = decode_row(p, m0 + r0 + 32 * i);
-      float4 v0[ROWS_PER_THREAD], v1[ROWS_PER_THREAD], v2[ROWS_PER_THREAD];   // 3 K blocks of loads in flight
-      auto gather = [&](int kb, float4 (&v)[ROWS_PER_THREAD]) {
+      // Register prefetch slots.  gather() ONLY issues loads (no instruction may read a loaded register before publish():
+      // even a predicated-off consumer stalls on the load's scoreboard and would serialise the loads); add / BN-ReLU
+      // prologue are applied in publish().  MODE 0: plain or channel-concat source, 3 K blocks in flight; MODE 1: second
+      // source added (x_i + y_{i-1}); MODE 2: per-channel affine(+ReLU) prologue; 2 K blocks in flight for 1 and 2.
+      Slot<MODE> sl0, sl1, sl2;
+      auto gather = [&](int kb, Slot<MODE>& sl) {
         const int k = kb * BK + chunk * 4;
         int ci = k, dt = 0, df = 0;
         if (!pointwise) {
@@ -201,14 +212,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           dt = kt * p.dT;
           df = (tap - kt * p.KF) * p.dF;
         }
-        const bool kok = k < p.K;
-        const bool second = (p.src2_mode == VP_SRC2_CONCAT) && (ci >= p.Cin);
+        const bool kok = k < p.K && !(a.debug & 2);
+        const bool second = (MODE == 0) && (p.src2_mode == VP_SRC2_CONCAT) && (ci >= p.Cin);
         const float* base = second ? p.src2 + p.src2_coff + (ci - p.Cin) : p.src + p.in_coff + ci;
         const int ld = second ? p.src2_ld : p.in_ld;
-        float4 ps = make_float4(1.f, 1.f, 1.f, 1.f), ph = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.pre_s != nullptr && kok) {
-          ps = __ldg(reinterpret_cast<const float4*>(p.pre_s + ci));
-          ph = __ldg(reinterpret_cast<const float4*>(p.pre_h + ci));
+        if constexpr (MODE == 2) {
+          sl.ps = make_float4(1.f, 1.f, 1.f, 1.f);
+          sl.ph = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kok) {
+            sl.ps = __ldg(reinterpret_cast<const float4*>(p.pre_s + ci));
+            sl.ph = __ldg(reinterpret_cast<const float4*>(p.pre_h + ci));
+          }
+          sl.okmask = 0;
         }
 #pragma unroll
         for (int i = 0; i < ROWS_PER_THREAD; ++i) {
@@ -219,23 +234,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             if (ti >= p.Tin) ti = 2 * (p.Tin - 1) - ti;
           }
           const bool ok = kok && rows[i].valid && ti >= 0 && ti < p.Tin && fi >= 0 && fi < p.Fin;
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok) {
-            const size_t row = (size_t)rows[i].base + (size_t)ti * p.Fin + fi;
-            x = __ldg(reinterpret_cast<const float4*>(base + row * ld));
-            if (p.src2_mode == VP_SRC2_ADD) {
-              const float4 u = __ldg(reinterpret_cast<const float4*>(p.src2 + row * p.src2_ld + p.src2_coff + ci));
-              x.x += u.x; x.y += u.y; x.z += u.z; x.w += u.w;
-            }
-            if (p.pre_s != nullptr) {
-              x.x = fmaf(x.x, ps.x, ph.x); x.y = fmaf(x.y, ps.y, ph.y); x.z = fmaf(x.z, ps.z, ph.z); x.w = fmaf(x.w, ps.w, ph.w);
-              if (p.pre_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-            }
+          const size_t row = ok ? (size_t)rows[i].base + (size_t)ti * p.Fin + fi : 0;
+          sl.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) sl.v[i] = __ldg(reinterpret_cast<const float4*>(base + row * ld));
+          if constexpr (MODE == 1) {
+            sl.u[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) sl.u[i] = __ldg(reinterpret_cast<const float4*>(p.src2 + row * p.src2_ld + p.src2_coff + ci));
           }
-          v[i] = x;
+          if constexpr (MODE == 2) sl.okmask |= ok ? (1u << i) : 0u;
         }
       };
-      auto publish = [&](int kb, float4 (&v)[ROWS_PER_THREAD]) {
+      constexpr int DEPTH = (MODE == 0) ? 3 : 2;
+      auto publish = [&](int kb, Slot<MODE>& sl) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         ++it;
@@ -246,23 +256,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         for (int i = 0; i < ROWS_PER_THREAD; ++i) {
           const int r = r0 + 32 * i;
           const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+          float4 x = sl.v[i];
+          if constexpr (MODE == 1) { x.x += sl.u[i].x; x.y += sl.u[i].y; x.z += sl.u[i].z; x.w += sl.u[i].w; }
+          if constexpr (MODE == 2) {
+            if (sl.okmask & (1u << i)) {              // zero padding stays zero: the conv pads the BN-ReLU'd map
+              x.x = fmaf(x.x, sl.ps.x, sl.ph.x); x.y = fmaf(x.y, sl.ps.y, sl.ph.y);
+              x.z = fmaf(x.z, sl.ps.z, sl.ph.z); x.w = fmaf(x.w, sl.ps.w, sl.ph.w);
+              if (p.pre_relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            }
+          }
           float4 hi, lo;
-          hi.x = tf32_rna(v[i].x); hi.y = tf32_rna(v[i].y); hi.z = tf32_rna(v[i].z); hi.w = tf32_rna(v[i].w);
-          lo.x = v[i].x - hi.x; lo.y = v[i].y - hi.y; lo.z = v[i].z - hi.z; lo.w = v[i].w - hi.w;
+          hi.x = tf32_rna(x.x); hi.y = tf32_rna(x.y); hi.z = tf32_rna(x.z); hi.w = tf32_rna(x.w);
+          lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
         }
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        mbar_arrive(full0 + 8 * s);
-        if (kb + 3 < a.k_blocks) gather(kb + 3, v);   // refill this register slot: 3 K blocks of loads stay in flight
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full0 + 8 * s);     // one arrival per producer warp
+        if (kb + DEPTH < a.k_blocks) gather(kb + DEPTH, sl);   // refill this slot: DEPTH K blocks of loads stay in flight
       };
-      gather(0, v0);
-      if (a.k_blocks > 1) gather(1, v1);
-      if (a.k_blocks > 2) gather(2, v2);
-      for (int kb = 0; kb < a.k_blocks; kb += 3) {
-        publish(kb, v0);
-        if (kb + 1 < a.k_blocks) publish(kb + 1, v1);
-        if (kb + 2 < a.k_blocks) publish(kb + 2, v2);
+      gather(0, sl0);
+      if (a.k_blocks > 1) gather(1, sl1);
+      if constexpr (DEPTH == 3) {
+        if (a.k_blocks > 2) gather(2, sl2);
+        for (int kb = 0; kb < a.k_blocks; kb += 3) {
+          publish(kb, sl0);
+          if (kb + 1 < a.k_blocks) publish(kb + 1, sl1);
+          if (kb + 2 < a.k_blocks) publish(kb + 2, sl2);
+        }
+      } else {
+        for (int kb = 0; kb < a.k_blocks; kb += 2) {
+          publish(kb, sl0);
+          if (kb + 1 < a.k_blocks) publish(kb + 1, sl1);
+        }
       }
     }
   } else if (warp == 4 + PRODUCER_WARPS) {
@@ -277,6 +304,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(empty0 + 8 * s, ph ^ 1);
+          if (a.debug & 1) { mbar_arrive(full0 + 8 * s); continue; }
           mbar_expect_tx(full0 + 8 * s, 2u * b_tile);          // the whole stage lands here (own slice + peers' multicasts)
           const uint32_t dst = smem_base + s * stage_bytes + 2u * A_TILE + crank * slice;
           if (C > 1) bulk_copy_g2s_mcast(dst, src + (size_t)kb * (2u * b_tile), slice, full0 + 8 * s, cmask);
@@ -301,6 +329,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           tc_fence_after();
           const uint32_t a_hi = smem_base + s * stage_bytes, a_lo = a_hi + A_TILE;
           const uint32_t b_hi = a_hi + 2u * A_TILE, b_lo = b_hi + b_tile;
+          if (!(a.debug & 4))
 #pragma unroll
           for (int kc = 0; kc < BK / 8; ++kc) {               // UMMA_K = 8 for tf32 = 32 bytes inside the swizzle row
             const uint64_t dah = smem_desc(a_hi + kc * 32), dal = smem_desc(a_lo + kc * 32);
@@ -326,20 +355,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const int cg = (lane & 7) * 4;           // this thread's 4 columns inside the chunk
     const int rsub = lane >> 3;              // rows rsub + 4*i
     const bool need_urow = (p.gate != nullptr) || (p.ubias != nullptr);
+    auto act4 = [](float4& v, int act) {     // called under a warp-uniform branch: one switch per float4, not per element
+      v.x = apply_act(v.x, act); v.y = apply_act(v.y, act); v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
+    };
     uint32_t tcount = 0;
     for (int g = cluster_id; g < total_groups; g += n_clusters, ++tcount) {
       const int acc = tcount & 1;
       const int mbase = ((g / a.n_tiles) * (int)C + (int)crank) * BM + warp * 32;
       const int n0 = (g % a.n_tiles) * BN;
+      // per-tile row state: output pointers, validity, per-utterance rows
+      float* optr[8];
       int urow[8];
+      uint32_t rowok = 0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int m = mbase + rsub + 4 * i;
-        urow[i] = (need_urow && m < p.M) ? urow_of(p, m) : 0;
+        const bool ok = m < p.M;
+        rowok |= ok ? (1u << i) : 0u;
+        optr[i] = p.dst + (size_t)(ok ? m : 0) * p.out_ld + p.out_coff + n0 + cg;
+        urow[i] = (need_urow && ok) ? urow_of(p, m) : 0;
       }
       mbar_wait(tfull0 + 8 * acc, (tcount >> 1) & 1);
       tc_fence_after();
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int n = n0 + c0 + cg;
+        const bool nok = n < p.N;
+        // per-column parameters first: their latency hides behind the TMEM load + transpose
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = b4;
+        if (nok) {
+          if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          if (p.post_s) {
+            s4 = __ldg(reinterpret_cast<const float4*>(p.post_s + n));
+            h4 = __ldg(reinterpret_cast<const float4*>(p.post_h + n));
+          }
+        }
         {
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), v);
@@ -354,39 +403,60 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                          : "memory");
         }
         __syncwarp();
-        const int n = n0 + c0 + cg;
-        if (n < p.N) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = b4;
-          if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-          if (p.post_s) {
-            s4 = __ldg(reinterpret_cast<const float4*>(p.post_s + n));
-            h4 = __ldg(reinterpret_cast<const float4*>(p.post_h + n));
-          }
+        if (nok) {
+          float4 v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int row = rsub + 4 * i;
-            const int m = mbase + row;
-            if (m < p.M) {
-              float4 v = *reinterpret_cast<const float4*>(pad + row * 36 + cg);
-              v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-              if (p.ubias) {
-                const float4 u = __ldg(reinterpret_cast<const float4*>(p.ubias + (size_t)urow[i] * p.N + n));
-                v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
-              }
-              if (p.act) { v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act); }
-              if (p.post_s) { v.x = fmaf(v.x, s4.x, h4.x); v.y = fmaf(v.y, s4.y, h4.y); v.z = fmaf(v.z, s4.z, h4.z); v.w = fmaf(v.w, s4.w, h4.w); }
-              if (p.gate) {
-                const float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)urow[i] * p.N + n));
-                v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
-              }
-              if (p.res) {
-                const float4 r = __ldg(reinterpret_cast<const float4*>(p.res + (size_t)m * p.res_ld + p.res_coff + n));
-                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-              }
-              if (p.act2) { v.x = apply_act(v.x, p.act2); v.y = apply_act(v.y, p.act2); v.z = apply_act(v.z, p.act2); v.w = apply_act(v.w, p.act2); }
-              *reinterpret_cast<float4*>(p.dst + (size_t)m * p.out_ld + p.out_coff + n) = v;
+            v[i] = *reinterpret_cast<const float4*>(pad + (rsub + 4 * i) * 36 + cg);
+            v[i].x += b4.x; v[i].y += b4.y; v[i].z += b4.z; v[i].w += b4.w;
+          }
+          if (p.ubias) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 u = __ldg(reinterpret_cast<const float4*>(p.ubias + (size_t)urow[i] * p.N + n));
+              v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
             }
           }
+          if (p.act == VP_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f); }
+          } else if (p.act != VP_ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) act4(v[i], p.act);
+          }
+          if (p.post_s) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[i].x = fmaf(v[i].x, s4.x, h4.x); v[i].y = fmaf(v[i].y, s4.y, h4.y);
+              v[i].z = fmaf(v[i].z, s4.z, h4.z); v[i].w = fmaf(v[i].w, s4.w, h4.w);
+            }
+          }
+          if (p.gate) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 gt = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)urow[i] * p.N + n));
+              v[i].x *= gt.x; v[i].y *= gt.y; v[i].z *= gt.z; v[i].w *= gt.w;
+            }
+          }
+          if (p.res) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (rowok & (1u << i)) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(p.res + (size_t)(mbase + rsub + 4 * i) * p.res_ld + p.res_coff + n));
+                v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
+              }
+            }
+          }
+          if (p.act2 == VP_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f); }
+          } else if (p.act2 != VP_ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) act4(v[i], p.act2);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (rowok & (1u << i)) *reinterpret_cast<float4*>(optr[i] + c0) = v[i];
         }
         __syncwarp();
       }
@@ -433,10 +503,15 @@ cudaError_t launch_conv_tc(const ConvParams& p, cudaStream_t stream) {
   a.m_tiles = (p.M + BM - 1) / BM;
   a.n_tiles = (p.N + a.BN - 1) / a.BN;
   a.k_blocks = (p.K + BK - 1) / BK;
+  static int debug_flags = -1;
+  if (debug_flags < 0) { const char* e = getenv("VPB_TC_DEBUG"); debug_flags = e ? atoi(e) : 0; }
+  a.debug = debug_flags;
   const size_t smem = (size_t)a.stages * stage_bytes + EPI_PAD_BYTES + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -466,7 +541,10 @@ cudaError_t launch_conv_tc(const ConvParams& p, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel, p, a);
+  cudaError_t e;
+  if (p.pre_s != nullptr) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, p, a);
+  else if (p.src2_mode == VP_SRC2_ADD) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, p, a);
+  else e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<0>, p, a);
   if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }

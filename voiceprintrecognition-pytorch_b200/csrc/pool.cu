@@ -147,11 +147,34 @@ __global__ void __launch_bounds__(256) asp_pool_smem_kernel(const __grid_constan
   const int c = blockIdx.x * 32 + lane;
   const int b = blockIdx.y;
   const bool ok = c < p.C;
-  const float* x = p.x + (size_t)b * p.T * p.x_ld + p.x_coff + c;
-  const float* l = p.logit + (size_t)b * p.T * p.l_ld + p.l_coff + c;
-  for (int t = wid; t < p.T; t += 8) {
-    sx[t * 32 + lane] = ok ? __ldg(x + (size_t)t * p.x_ld) : 0.f;
-    sl[t * 32 + lane] = ok ? __ldg(l + (size_t)t * p.l_ld) : 0.f;
+  {
+    // stage the strips: 8 lanes x float4 cover one 128-byte row, 32 rows per pass, 4 passes of loads in flight
+    const int c4 = (threadIdx.x & 7) * 4;
+    const int cc = blockIdx.x * 32 + c4;
+    const bool cok = cc < p.C;                      // C % 4 == 0 on this path (checked by the launcher)
+    const float* xb = p.x + (size_t)b * p.T * p.x_ld + p.x_coff + cc;
+    const float* lb = p.logit + (size_t)b * p.T * p.l_ld + p.l_coff + cc;
+    for (int t0 = threadIdx.x >> 3; t0 < p.T; t0 += 128) {
+      float4 xv[4], lv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + 32 * u;
+        xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        lv[u] = xv[u];
+        if (cok && t < p.T) {
+          xv[u] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)t * p.x_ld));
+          lv[u] = __ldg(reinterpret_cast<const float4*>(lb + (size_t)t * p.l_ld));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + 32 * u;
+        if (t < p.T) {
+          *reinterpret_cast<float4*>(sx + t * 32 + c4) = xv[u];
+          *reinterpret_cast<float4*>(sl + t * 32 + c4) = lv[u];
+        }
+      }
+    }
   }
   __syncthreads();
   auto block_reduce = [&](float v, bool is_max) -> float {
@@ -197,7 +220,7 @@ __global__ void __launch_bounds__(256) asp_pool_smem_kernel(const __grid_constan
 cudaError_t launch_asp_pool(const AspParams& p, cudaStream_t stream) {
   dim3 grid((p.C + 31) / 32, p.B);
   const size_t smem = (size_t)p.T * 32 * 2 * sizeof(float);
-  if (smem <= 200 * 1024) {
+  if (smem <= 200 * 1024 && (p.C & 3) == 0 && (p.x_ld & 3) == 0 && (p.x_coff & 3) == 0 && (p.l_ld & 3) == 0 && (p.l_coff & 3) == 0) {
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
       cudaError_t e = cudaFuncSetAttribute(asp_pool_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
