@@ -192,17 +192,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const int r0 = t >> 3;                 // 0..31
     const bool pointwise = (p.KT * p.KF == 1);
     uint32_t it = 0;
-    for (int g = cluster_id; g < total_groups; g += n_clusters) {
-      const int m0 = ((g / a.n_tiles) * (int)C + (int)crank) * BM;
-      RowInfo rows[ROWS_PER_THREAD];
-#pragma unroll
-      for (int i = 0; i < ROWS_PER_THREAD; ++i) rows[i] = decode_row(p, m0 + r0 + 32 * i);
+    // The (tile, K block) pairs of this CTA form ONE flat stream: the gather cursor runs DEPTH items ahead of the publish
+    // cursor and crosses tile boundaries, so the load pipeline never drains between tiles.
+    const int my_tiles = (total_groups - cluster_id + n_clusters - 1) / n_clusters;
+    const int total_items = my_tiles * a.k_blocks;
+    RowInfo rows[ROWS_PER_THREAD];
+    int rows_tile = -1;
+    {
       // Register prefetch slots.  gather() ONLY issues loads (no instruction may read a loaded register before publish():
       // even a predicated-off consumer stalls on the load's scoreboard and would serialise the loads); add / BN-ReLU
       // prologue are applied in publish().  MODE 0: plain or channel-concat source, 3 K blocks in flight; MODE 1: second
       // source added (x_i + y_{i-1}); MODE 2: per-channel affine(+ReLU) prologue; 2 K blocks in flight for 1 and 2.
       Slot<MODE> sl0, sl1, sl2;
-      auto gather = [&](int kb, Slot<MODE>& sl) {
+      auto gather = [&](int q, Slot<MODE>& sl) {
+        const int tl = q / a.k_blocks;
+        const int kb = q - tl * a.k_blocks;
+        if (tl != rows_tile) {                 // gather cursor entered a new tile: decode its 4 rows
+          rows_tile = tl;
+          const int g = cluster_id + tl * n_clusters;
+          const int m0 = ((g / a.n_tiles) * (int)C + (int)crank) * BM;
+#pragma unroll
+          for (int i = 0; i < ROWS_PER_THREAD; ++i) rows[i] = decode_row(p, m0 + r0 + 32 * i);
+        }
         const int k = kb * BK + chunk * 4;
         int ci = k, dt = 0, df = 0;
         if (!pointwise) {
@@ -245,7 +256,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
       };
       constexpr int DEPTH = (MODE == 0) ? 3 : 2;
-      auto publish = [&](int kb, Slot<MODE>& sl) {
+      auto publish = [&](int q, Slot<MODE>& sl) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         ++it;
@@ -274,21 +285,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(full0 + 8 * s);     // one arrival per producer warp
-        if (kb + DEPTH < a.k_blocks) gather(kb + DEPTH, sl);   // refill this slot: DEPTH K blocks of loads stay in flight
+        if (q + DEPTH < total_items) gather(q + DEPTH, sl);   // refill this slot: DEPTH K blocks of loads stay in flight
       };
-      gather(0, sl0);
-      if (a.k_blocks > 1) gather(1, sl1);
+      if (total_items > 0) gather(0, sl0);
+      if (total_items > 1) gather(1, sl1);
       if constexpr (DEPTH == 3) {
-        if (a.k_blocks > 2) gather(2, sl2);
-        for (int kb = 0; kb < a.k_blocks; kb += 3) {
-          publish(kb, sl0);
-          if (kb + 1 < a.k_blocks) publish(kb + 1, sl1);
-          if (kb + 2 < a.k_blocks) publish(kb + 2, sl2);
+        if (total_items > 2) gather(2, sl2);
+        for (int q = 0; q < total_items; q += 3) {
+          publish(q, sl0);
+          if (q + 1 < total_items) publish(q + 1, sl1);
+          if (q + 2 < total_items) publish(q + 2, sl2);
         }
       } else {
-        for (int kb = 0; kb < a.k_blocks; kb += 2) {
-          publish(kb, sl0);
-          if (kb + 1 < a.k_blocks) publish(kb + 1, sl1);
+        for (int q = 0; q < total_items; q += 2) {
+          publish(q, sl0);
+          if (q + 1 < total_items) publish(q + 1, sl1);
         }
       }
     }

@@ -175,7 +175,7 @@ class MVectorPredictor:
 
     #: utterances per pipeline chunk of predict_batch (host gather + H2D of chunk k+1 overlap the kernels of chunk k)
     CHUNK = int(os.environ.get('VPB_PREDICT_CHUNK', '128'))
-    GATHER_THREADS = 4
+    GATHER_THREADS = int(os.environ.get('VPB_GATHER_THREADS', '4'))
 
     def _pinned_slot(self, slot, n):
         """Two reusable pinned host staging buffers (double buffering)."""
@@ -208,6 +208,13 @@ class MVectorPredictor:
         D = self.predictor.embd_dim
         emb = torch.empty(B, D, dtype=torch.float32, device=dev)
         cb = min(self.CHUNK, B)
+        # chunk schedule: a short first chunk gets the GPU busy early (its host gather + H2D are the only exposed copies),
+        # then full chunks; [cb/4, 3cb/4, cb, cb, ...]
+        bounds = [0]
+        if B > cb and cb >= 64:
+            bounds += [cb // 4, cb]
+        while bounds[-1] < B:
+            bounds.append(min(bounds[-1] + cb, B))
         feats = torch.empty(cb * T * F, dtype=torch.float32, device=dev)
         scratch = torch.empty(max(int(L.lib().vp_frontend_scratch_floats(eng.handle, cb, lmax)), 1), dtype=torch.float32,
                               device=dev)
@@ -216,8 +223,8 @@ class MVectorPredictor:
             self._copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
         free_ev = [None, None]                       # compute finished reading device/pinned slot
-        for ci, lo in enumerate(range(0, B, cb)):
-            hi = min(lo + cb, B)
+        for ci in range(len(bounds) - 1):
+            lo, hi = bounds[ci], bounds[ci + 1]
             n = hi - lo
             slot = ci & 1
             if free_ev[slot] is not None:
