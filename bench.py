@@ -149,23 +149,35 @@ def run_reference_arm(args):
 # clocks
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line): started before the warm-up so that it is
+    already streaming, every sample carries a timestamp and only those inside [t0, t1] (the timed region) are used."""
+    Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         self.p = None
+        self.t0 = self.t1 = None
         try:
             self.p = subprocess.Popen(['nvidia-smi', f'--id={gpu_index}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       '-lms', '20'], stdout=self.f, stderr=subprocess.DEVNULL)
+            time.sleep(1.0)                      # let it start streaming
         except Exception:
             self.p = None
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
         if self.p is None:
             return out
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -173,23 +185,29 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        rows = []
         for ln in self.f.read().splitlines():
             c = [x.strip() for x in ln.split(',')]
             if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                rows.append((ts, float(c[1]), float(c[2]), c[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), c[5:9]):
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+        window = 'timed region'
+        if len(inside) < 2:                      # region shorter than the sampling period: widen to warm-up + region
+            inside, window = rows, 'warm-up + timed region'
+        reasons = set()
+        for _, _, _, flags in inside:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), flags):
                 if v.lower().startswith('active'):
                     reasons.add(name)
-        if sm:
-            # under-load samples only: the upper half of what was seen during the region
-            sm_sorted = sorted(sm)
-            out = {'sm_mhz': statistics.median(sm_sorted[len(sm_sorted) // 2:]), 'sm_max_mhz': max(mx),
-                   'reasons': sorted(reasons), 'samples': len(sm)}
+        if inside:
+            sm = sorted(r[1] for r in inside)
+            out = {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(r[2] for r in inside), 'reasons': sorted(reasons),
+                   'samples': len(inside), 'window': window}
         try:
             os.unlink(self.f.name)
         except OSError:
@@ -263,16 +281,20 @@ def run_gpu_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(step_fn, steps, warmup):
+    def timed(step_fn, steps, warmup, sampler=None):
         for i in range(warmup):
             step_fn(i)
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.mark_start()
         e0.record()
         for i in range(steps):
             step_fn(warmup + i)
         e1.record()
         sync_all()
+        if sampler:
+            sampler.mark_end()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -280,7 +302,7 @@ def run_gpu_arm(args):
 
     mark('programs built, starting timed region')
     clocks = ClockSampler(local) if rank == 0 else None
-    ms_res = timed(step_resident, args.steps, args.warmup)
+    ms_res = timed(step_resident, args.steps, args.warmup, clocks)
     clk = clocks.stop() if clocks else None
     mark(f'resident timing done: {ms_res:.2f} ms')
     if os.environ.get('VPB_E2E_ONLY'):
@@ -385,7 +407,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--light', action='store_true', help='resident-input timing only (for runs under ncu): no e2e / '
