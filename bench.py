@@ -257,7 +257,9 @@ def run_gpu_arm(args):
     from mvector import _lib as L
     pool_host = [synth_waves(B, 1234 + 100 * rank + i).pin_memory() for i in range(N_POOL)]
     pool_dev = [w.to(dev) for w in pool_host]
-    pool_np = [[w[i].numpy() for i in range(B)] for w in pool_host]     # list-of-arrays view for predict_batch
+    # predict_batch input: a list of INDEPENDENTLY allocated pageable numpy arrays (like decoded audio files), not views
+    # of one pinned matrix
+    pool_np = [[np.array(w[i].numpy(), copy=True) for i in range(B)] for w in pool_host]
     feats = torch.empty(B * T * 80, dtype=torch.float32, device=dev)
     scratch = torch.empty(max(int(L.lib().vp_frontend_scratch_floats(fz.engine.handle, B, SAMPLES)), 1),
                           dtype=torch.float32, device=dev)

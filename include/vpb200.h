@@ -157,6 +157,10 @@ int vp_embed_wave(vp_program* p, const float* wave, int32_t B, int32_t Lpad, con
 int vp_embed_profiled(vp_program* p, const float* feats, float* emb, void* stream, float* ms_per_op);
 /* op i of the program: kind, GEMM view (M rows, N = Cout, K = taps*Cin; K = 0 for non-conv ops), resolved engine */
 int vp_program_op_info(const vp_program* p, int32_t i, int32_t* kind, int64_t* M, int64_t* N, int64_t* K, int32_t* engine);
+/* Host utility (no CUDA): gather n waveforms (host pointers srcs[i], lens[i] samples) into the zero-padded row-major
+ * staging matrix dst[n, lmax] with n_threads worker threads -- the pad-to-longest loop of predict.py:248-254. */
+int vp_host_gather_pad(const float* const* srcs, const int32_t* lens, int32_t n, int32_t lmax, float* dst,
+                       int32_t n_threads);
 /* number of kernel launches one vp_embed enqueues (bench.py's gpu_launches) */
 int32_t vp_program_launches(const vp_program* p);
 /* debugging / tests: copy a workspace region to a caller device buffer on the stream */

@@ -251,3 +251,65 @@ def test_c2_full_batch_properties():
     idx = [0, 100, 255]
     ref = om.forward('EcapaTdnn', sd, ofe.featurize(wave_[idx], None, 'Fbank', fargs), **margs).numpy()
     assert rel_l2(e[idx].cpu().numpy(), ref).max() < EMB_TOL
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE configs 3-5
+def _ragged(lens, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [(torch.randn(n, generator=g) * 0.1).numpy() for n in lens]
+
+
+def test_c3_campplus_fbank_batch():
+    """BASELINE config #3 (per-GPU shard shape, reduced batch): CAM++ + Fbank-80 on 3 s utterances, waveform -> embedding."""
+    from oracle import frontend as ofe
+    from oracle import models as om
+    margs, fargs = dict(embd_dim=192), dict(sample_frequency=16000, num_mel_bins=80)
+    sd = om.random_state_dict('CAMPPlus', 80, seed=5, **margs)
+    waves = _ragged([48000] * 6, 31)
+    x, ratio = ofe.pad_batch(waves)
+    ref = om.forward('CAMPPlus', sd, ofe.featurize(x, ratio, 'Fbank', fargs), **margs).numpy()
+    fz = _featurizer(dict(feature_method='Fbank', method_args=fargs))
+    got = _model('CAMPPlus', 80, margs, sd)(fz(torch.from_numpy(x), torch.from_numpy(ratio))).cpu().numpy()
+    assert rel_l2(got, ref).max() < EMB_TOL
+
+
+def test_c4_resnetse_melspectrogram_5s():
+    """BASELINE config #4: ResNetSE + MelSpectrogram (README.md:303-311 method_args; the shipped yml's Fbank args make
+    MelSpectrogram(**args) raise TypeError, SURVEY.md finding 3), 5 s @ 16 kHz -> [B, 251, 64]."""
+    import warnings
+    from oracle import frontend as ofe
+    from oracle import models as om
+    fargs = dict(sample_rate=16000, n_fft=1024, win_length=1024, hop_length=320, f_min=50.0, f_max=14000.0, n_mels=64)
+    margs = dict(embd_dim=192, pooling_type='ASP')
+    sd = om.random_state_dict('ResNetSE', 64, seed=6, gain=om.CONDITIONED_GAIN['ResNetSE'], **margs)
+    waves = _ragged([80000] * 3, 32)
+    x, ratio = ofe.pad_batch(waves)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        feats = ofe.featurize(x, ratio, 'MelSpectrogram', fargs)
+        fz = _featurizer(dict(feature_method='MelSpectrogram', method_args=fargs))
+    assert feats.shape == (3, 251, 64)
+    # raw power mel features (no log) have a huge dynamic range; scale like a dB-normalised recording keeps them finite
+    ref = om.forward('ResNetSE', sd, feats, **margs).numpy()
+    got = _model('ResNetSE', 64, margs, sd)(fz(torch.from_numpy(x), torch.from_numpy(ratio))).cpu().numpy()
+    assert rel_l2(got, ref).max() < EMB_TOL
+    with pytest.raises(TypeError):                       # the shipped configs/resnet_se.yml method_args
+        _featurizer(dict(feature_method='MelSpectrogram', method_args=dict(sample_frequency=16000, num_mel_bins=80)))
+
+
+def test_c5_eres2net55m_ragged_1_to_10s():
+    """BASELINE config #5: the 55.2 M ERes2Net (m_channels=64, mul_channel=2, expansion=4, base_width=24, scale=3) on a
+    ragged 1-10 s batch padded to its max (reference ragged semantics: T from Lmax, masked frames are zeros)."""
+    from oracle import frontend as ofe
+    from oracle import models as om
+    margs = dict(embd_dim=192, m_channels=64, mul_channel=2, expansion=4, base_width=24, scale=3)
+    fargs = dict(sample_frequency=16000, num_mel_bins=80)
+    sd = om.random_state_dict('ERes2Net', 80, seed=8, gain=om.CONDITIONED_GAIN['ERes2Net'], **margs)
+    waves = _ragged([16000, 160000], 33)
+    x, ratio = ofe.pad_batch(waves)
+    feats = ofe.featurize(x, ratio, 'Fbank', fargs)
+    assert feats.shape == (2, 998, 80)
+    ref = om.forward('ERes2Net', sd, feats, **margs).numpy()
+    fz = _featurizer(dict(feature_method='Fbank', method_args=fargs))
+    got = _model('ERes2Net', 80, margs, sd)(fz(torch.from_numpy(x), torch.from_numpy(ratio))).cpu().numpy()
+    assert rel_l2(got, ref).max() < EMB_TOL

@@ -45,10 +45,10 @@ def test_pack_tc_image_roundtrip():
     chunk permutation gives back the zero-padded [n_tile][k_block][BN][32] tiles."""
     from mvector.engine import pack_tc, tc_tile_n, tf32_rna
     rng = np.random.default_rng(0)
-    for N, K in ((512, 512), (192, 400), (128, 1536), (32, 384), (24, 72)):
+    for N, K in ((512, 512), (192, 400), (128, 1536), (32, 384), (24, 72), (512, 2304)):
         W = rng.standard_normal((N, K)).astype(np.float32)
         img, bn = pack_tc(W.astype(np.float64))
-        assert bn == tc_tile_n(N) and bn % 16 == 0 and bn <= 256
+        assert bn == tc_tile_n(N, K) and bn % 16 == 0 and bn <= 256
         nt, kb = -(-N // bn), -(-K // 32)
         t = img.reshape(nt, kb, 2, bn, 8, 4)
         r = np.arange(bn)[:, None]

@@ -123,12 +123,26 @@ template <> struct Slot<0> { float4 v[ROWS_PER_THREAD]; };
 template <> struct Slot<1> { float4 v[ROWS_PER_THREAD]; float4 u[ROWS_PER_THREAD]; };
 template <> struct Slot<2> { float4 v[ROWS_PER_THREAD]; float4 ps, ph; uint32_t okmask; };
 
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]),
+      "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]), "f"(v[20]),
+      "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]),
+      "f"(v[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 struct TcArgs {
   const float* w_tc;     // pre-split, pre-tiled, pre-swizzled weights: [n_tile][k_block][hi BN x 128 B | lo BN x 128 B]
   int BN;                // N tile (multiple of 16, <= 256)
   int stages;
   int tmem_cols;         // power of two >= 2*BN
   int m_tiles, n_tiles, k_blocks;
+  int kc, n_chunks;      // K blocks per accumulation chunk / chunks per tile (long-K layers: bounded accumulation length)
   int debug;             // experiments only (VPB_TC_DEBUG): 1 = skip B copies, 2 = skip A global loads, 4 = skip MMAs
 };
 
@@ -328,31 +342,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     if (lane == 0) {
       // kind::tf32 instruction descriptor: D=F32 (bit 4), A=B=TF32 (2 at bits 7 and 10), K-major, N>>3 @17, M>>4 @24
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      uint32_t it = 0, tcount = 0;
-      for (int g = cluster_id; g < total_groups; g += n_clusters, ++tcount) {
-        const int acc = tcount & 1;
-        mbar_wait(tempty0 + 8 * acc, ((tcount >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < a.k_blocks; ++kb, ++it) {
-          const int s = it % S;
-          mbar_wait(full0 + 8 * s, (it / S) & 1);
+      uint32_t it = 0, ccount = 0;
+      for (int g = cluster_id; g < total_groups; g += n_clusters) {
+        // Long-K layers are accumulated in chunks of `kc` K blocks, each into a fresh TMEM accumulator; the epilogue
+        // warps fold the chunks into a running fp32 sum with correctly rounded adds.  (The tensor core truncates on every
+        // accumulate; the bias grows linearly with the number of accumulates: 4.8e-5 at K=1536, measured.)
+        for (int ch = 0; ch < a.n_chunks; ++ch, ++ccount) {
+          const int acc = ccount & 1;
+          mbar_wait(tempty0 + 8 * acc, ((ccount >> 1) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t a_hi = smem_base + s * stage_bytes, a_lo = a_hi + A_TILE;
-          const uint32_t b_hi = a_hi + 2u * A_TILE, b_lo = b_hi + b_tile;
-          if (!(a.debug & 4))
+          const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+          const int kb0 = ch * a.kc;
+          const int kb1 = (kb0 + a.kc < a.k_blocks) ? kb0 + a.kc : a.k_blocks;
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const int s = it % S;
+            mbar_wait(full0 + 8 * s, (it / S) & 1);
+            tc_fence_after();
+            const uint32_t a_hi = smem_base + s * stage_bytes, a_lo = a_hi + A_TILE;
+            const uint32_t b_hi = a_hi + 2u * A_TILE, b_lo = b_hi + b_tile;
+            if (!(a.debug & 4))
 #pragma unroll
-          for (int kc = 0; kc < BK / 8; ++kc) {               // UMMA_K = 8 for tf32 = 32 bytes inside the swizzle row
-            const uint64_t dah = smem_desc(a_hi + kc * 32), dal = smem_desc(a_lo + kc * 32);
-            const uint64_t dbh = smem_desc(b_hi + kc * 32), dbl = smem_desc(b_lo + kc * 32);
-            umma_tf32(d, dal, dbh, idesc, (kb | kc) != 0);
-            umma_tf32(d, dah, dbl, idesc, 1);
-            umma_tf32(d, dah, dbh, idesc, 1);
+            for (int kc = 0; kc < BK / 8; ++kc) {             // UMMA_K = 8 for tf32 = 32 bytes inside the swizzle row
+              const uint64_t dah = smem_desc(a_hi + kc * 32), dal = smem_desc(a_lo + kc * 32);
+              const uint64_t dbh = smem_desc(b_hi + kc * 32), dbl = smem_desc(b_lo + kc * 32);
+              umma_tf32(d, dal, dbh, idesc, (kb != kb0) || (kc != 0));
+              umma_tf32(d, dah, dbl, idesc, 1);
+              umma_tf32(d, dah, dbh, idesc, 1);
+            }
+            if (C > 1) umma_commit_mcast(empty0 + 8 * s, cmask);   // frees the stage in every CTA of the cluster
+            else umma_commit(empty0 + 8 * s);                 // frees the smem stage when these MMAs retire
           }
-          if (C > 1) umma_commit_mcast(empty0 + 8 * s, cmask);   // frees the stage in every CTA of the cluster
-          else umma_commit(empty0 + 8 * s);                   // frees the smem stage when these MMAs retire
+          umma_commit(tfull0 + 8 * acc);                      // chunk accumulator ready for the epilogue warps
         }
-        umma_commit(tfull0 + 8 * acc);                        // accumulator ready for the epilogue
       }
     }
   } else {
@@ -369,9 +390,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     auto act4 = [](float4& v, int act) {     // called under a warp-uniform branch: one switch per float4, not per element
       v.x = apply_act(v.x, act); v.y = apply_act(v.y, act); v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
     };
-    uint32_t tcount = 0;
-    for (int g = cluster_id; g < total_groups; g += n_clusters, ++tcount) {
-      const int acc = tcount & 1;
+    uint32_t ccount = 0;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t run_col = (uint32_t)(2 * BN);   // running-sum accumulator (only when n_chunks > 1)
+    for (int g = cluster_id; g < total_groups; g += n_clusters) {
       const int mbase = ((g / a.n_tiles) * (int)C + (int)crank) * BM + warp * 32;
       const int n0 = (g % a.n_tiles) * BN;
       // per-tile row state: output pointers, validity, per-utterance rows
@@ -386,7 +408,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         optr[i] = p.dst + (size_t)(ok ? m : 0) * p.out_ld + p.out_coff + n0 + cg;
         urow[i] = (need_urow && ok) ? urow_of(p, m) : 0;
       }
-      mbar_wait(tfull0 + 8 * acc, (tcount >> 1) & 1);
+      // fold all but the last accumulation chunk into the running sum (TMEM columns [2BN, 3BN))
+      for (int ch = 0; ch + 1 < a.n_chunks; ++ch, ++ccount) {
+        const int accf = ccount & 1;
+        mbar_wait(tfull0 + 8 * accf, (ccount >> 1) & 1);
+        tc_fence_after();
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_base + lane_base + (uint32_t)(accf * BN + c0), v);
+          if (ch > 0) {
+            float r[32];
+            tmem_ld32(tmem_base + lane_base + run_col + (uint32_t)c0, r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += r[j];
+          }
+          tmem_st32(tmem_base + lane_base + run_col + (uint32_t)c0, v);
+        }
+        tc_fence_before();
+        mbar_arrive(tempty0 + 8 * accf);
+      }
+      const int acc = ccount & 1;
+      mbar_wait(tfull0 + 8 * acc, (ccount >> 1) & 1);
+      ++ccount;
       tc_fence_after();
       for (int c0 = 0; c0 < BN; c0 += 32) {
         const int n = n0 + c0 + cg;
@@ -402,7 +445,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
         {
           float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+          tmem_ld32(tmem_base + lane_base + (uint32_t)(acc * BN + c0), v);
+          if (a.n_chunks > 1) {
+            float r[32];
+            tmem_ld32(tmem_base + lane_base + run_col + (uint32_t)c0, r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += r[j];
+          }
           if (c0 + 32 >= BN) {                // last read of this accumulator buffer: hand it back to the MMA warp
             tc_fence_before();
             mbar_arrive(tempty0 + 8 * acc);
@@ -486,8 +535,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 }  // namespace tc
 
 // Host-visible tiling rule (mirrored by the Python packer mvector/engine.py::tc_tile_n).
-static int tc_tile_n(int N) {
-  if (N >= 256) return 256;
+// Layers with K > 1536 are accumulated in chunks (see the MMA issuer) and need a third TMEM accumulator -> N tile <= 128.
+static const int KC_BLOCKS = 16;           // 512 K elements per accumulation chunk
+static bool tc_chunked(int K) { return K > 1536; }
+static int tc_tile_n(int N, int K) {
+  if (N >= 256 && !tc_chunked(K)) return 256;
+  if (N >= 128) return 128;
   return (N + 15) & ~15;
 }
 
@@ -495,7 +548,7 @@ bool conv_tc_supported(const ConvParams& p) {
   if (p.w_tc == nullptr) return false;
   if (p.M < 1024) return false;                       // tiny-M ops (SE / ASP bias / final FC) stay on the exact FFMA engine
   if (p.N < 16 || (p.N & 3) || (p.K & 3)) return false;
-  if (p.tc_bn != tc_tile_n(p.N)) return false;
+  if (p.tc_bn != tc_tile_n(p.N, p.K)) return false;
   return true;
 }
 
@@ -508,12 +561,15 @@ cudaError_t launch_conv_tc(const ConvParams& p, cudaStream_t stream) {
   a.stages = SMEM_BUDGET / stage_bytes;
   if (a.stages > 8) a.stages = 8;
   if (a.stages < 2) return cudaErrorInvalidConfiguration;
-  int cols = 32;
-  while (cols < 2 * a.BN) cols <<= 1;
-  a.tmem_cols = cols;
   a.m_tiles = (p.M + BM - 1) / BM;
   a.n_tiles = (p.N + a.BN - 1) / a.BN;
   a.k_blocks = (p.K + BK - 1) / BK;
+  a.kc = tc_chunked(p.K) ? KC_BLOCKS : a.k_blocks;
+  a.n_chunks = (a.k_blocks + a.kc - 1) / a.kc;
+  int cols = 32;
+  while (cols < (a.n_chunks > 1 ? 3 : 2) * a.BN) cols <<= 1;
+  if (cols > 512) return cudaErrorInvalidConfiguration;
+  a.tmem_cols = cols;
   static int debug_flags = -1;
   if (debug_flags < 0) { const char* e = getenv("VPB_TC_DEBUG"); debug_flags = e ? atoi(e) : 0; }
   a.debug = debug_flags;

@@ -77,6 +77,7 @@ def lib():
         'vp_embed_profiled': (C.c_int, [vp, f32p, f32p, vp, C.c_void_p]),
         'vp_program_op_info': (C.c_int, [vp, i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
         'vp_program_peek': (C.c_int, [vp, C.c_int64, sz, C.c_void_p, vp]),
+        'vp_host_gather_pad': (C.c_int, [C.c_void_p, C.c_void_p, i32, i32, C.c_void_p, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError here = header/library mismatch
@@ -93,4 +94,4 @@ def lib():
 EXPORTS = ['vp_abi_version', 'vp_sizeof_op', 'vp_sizeof_frontend_desc', 'vp_create', 'vp_destroy', 'vp_last_error',
            'vp_frontend_set', 'vp_num_frames', 'vp_frontend_scratch_floats', 'vp_fbank', 'vp_melspec',
            'vp_weights_load', 'vp_program_create', 'vp_program_destroy', 'vp_embed', 'vp_embed_wave',
-           'vp_program_launches', 'vp_program_peek', 'vp_embed_profiled', 'vp_program_op_info']
+           'vp_program_launches', 'vp_program_peek', 'vp_embed_profiled', 'vp_program_op_info', 'vp_host_gather_pad']

@@ -93,9 +93,14 @@ class WeightArena:
         return np.concatenate(self._chunks) if self._chunks else np.zeros(64, dtype=np.float32)
 
 
-def tc_tile_n(N):
-    """N tile of the tcgen05 engine (must match conv_tc.cu::tc_tile_n)."""
-    return 256 if N >= 256 else (N + 15) // 16 * 16
+def tc_tile_n(N, K=0):
+    """N tile of the tcgen05 engine (must match conv_tc.cu::tc_tile_n): 256-wide tiles, except for long-K layers
+    (K > 1536) whose chunked accumulation keeps a third TMEM accumulator and therefore uses 128-wide tiles."""
+    if N >= 256 and K <= 1536:
+        return 256
+    if N >= 128:
+        return 128
+    return (N + 15) // 16 * 16
 
 
 def tf32_rna(x):
@@ -108,7 +113,7 @@ def pack_tc(W):
     """[N, K] -> (float32 image [n_tiles, k_blocks, 2(hi|lo), BN, 32] with SWIZZLE_128B chunk permutation, BN).
     hi = tf32(W), lo = W - hi (exact in fp32).  Rows >= N / columns >= K are zero."""
     N, K = W.shape
-    bn = tc_tile_n(N)
+    bn = tc_tile_n(N, K)
     nt, kb = (N + bn - 1) // bn, (K + 31) // 32
     Wp = np.zeros((nt * bn, kb * 32), dtype=np.float32)
     Wp[:N, :K] = W.astype(np.float32)

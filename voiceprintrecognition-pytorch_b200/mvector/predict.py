@@ -11,6 +11,7 @@ Differences that are deliberate:
   * ``speaker_diarization`` (predict.py:365-395: VAD + spectral clustering on CPU) is outside the hot path and raises
     NotImplementedError.
 """
+import ctypes as C
 import os
 import pickle
 import shutil
@@ -58,7 +59,6 @@ class MVectorPredictor:
         self.predictor.eval()
         self._pinned = None
         self._copy_stream = None
-        self._pool = None
 
         self.audio_feature = None
         self.audio_feature_mean = None
@@ -175,7 +175,7 @@ class MVectorPredictor:
 
     #: utterances per pipeline chunk of predict_batch (host gather + H2D of chunk k+1 overlap the kernels of chunk k)
     CHUNK = int(os.environ.get('VPB_PREDICT_CHUNK', '128'))
-    GATHER_THREADS = int(os.environ.get('VPB_GATHER_THREADS', '4'))
+    GATHER_THREADS = int(os.environ.get('VPB_GATHER_THREADS', '8'))
 
     def _pinned_slot(self, slot, n):
         """Two reusable pinned host staging buffers (double buffering)."""
@@ -230,22 +230,12 @@ class MVectorPredictor:
             if free_ev[slot] is not None:
                 free_ev[slot].synchronize()          # pinned slot may be overwritten only after its H2D + kernels
             host = self._pinned_slot(slot, n * lmax).view(n, lmax)
-            hnp = host.numpy()
-            def fill(r0, r1, hnp=hnp, lo=lo):          # zero padding to the global longest item (predict.py:248-254)
-                for i in range(r0, r1):
-                    w = waves[lo + i]
-                    m = w.shape[0]
-                    hnp[i, :m] = w
-                    if m < lmax:
-                        hnp[i, m:] = 0.0
-            if n >= 32 and self.GATHER_THREADS > 1:   # numpy releases the GIL while copying: gather with a few threads
-                if self._pool is None:
-                    from concurrent.futures import ThreadPoolExecutor
-                    self._pool = ThreadPoolExecutor(max_workers=self.GATHER_THREADS)
-                step = -(-n // self.GATHER_THREADS)
-                list(self._pool.map(lambda r: fill(r, min(r + step, n)), range(0, n, step)))
-            else:
-                fill(0, n)
+            # zero padding to the global longest item (predict.py:248-254): native multi-threaded gather (GIL released)
+            ptrs = (C.c_void_p * n)(*[w.ctypes.data for w in waves[lo:hi]])
+            lens = (C.c_int32 * n)(*[w.shape[0] for w in waves[lo:hi]])
+            rc = L.lib().vp_host_gather_pad(ptrs, lens, n, lmax, C.c_void_p(host.data_ptr()), self.GATHER_THREADS)
+            if rc != 0:
+                raise RuntimeError(f'vp_host_gather_pad failed ({rc})')
             dw = dwave[slot][:n * lmax].view(n, lmax)
             with torch.cuda.stream(self._copy_stream):
                 dw.copy_(host, non_blocking=True)
@@ -267,7 +257,8 @@ class MVectorPredictor:
 
     def predict_batch(self, audios_data, sample_rate=16000, batch_size=32):
         """预测一批音频的特征 (predict.py:231-265) -> np.ndarray [B, embd_dim], order preserved."""
-        waves = [self._load_audio(audio_data=a, sample_rate=sample_rate).samples for a in audios_data]
+        waves = [np.ascontiguousarray(self._load_audio(audio_data=a, sample_rate=sample_rate).samples, dtype=np.float32)
+                 for a in audios_data]
         lmax = max(w.shape[0] for w in waves)
         return self._embed_waves(waves, lmax, masked=True)
 
