@@ -93,7 +93,7 @@ enum {                       /* vp_op.kind */
   VP_OP_CONV = 1,            /* implicit-GEMM conv1d/conv2d/linear with fused prologue + epilogue */
   VP_OP_CONV_C1 = 2,         /* 3x3 conv2d with Cin = 1 on the feature map [B,T,F] -> [B,T,F,C] */
   VP_OP_COLSTATS = 3,        /* per-utterance column statistics over rows (mean / mean+std variants / segments) */
-  VP_OP_ASP_POOL = 4,        /* softmax over T of logits, attentive mean + std (pooling.py:122-126) */
+  VP_OP_ASP_POOL = 4,        /* softmax over T of logits, attentive mean + std (pooling.py:122-126); mode 1 = mean only (SAP, pooling.py:62-64) */
   VP_OP_EW = 5               /* elementwise: gate*x + residual, AFF blend, copy */
 };
 enum { VP_ACT_NONE = 0, VP_ACT_RELU = 1, VP_ACT_HARDTANH20 = 2, VP_ACT_SIGMOID = 3, VP_ACT_TANH = 4, VP_ACT_SILU = 5 };
@@ -104,7 +104,8 @@ enum {                       /* VP_OP_COLSTATS modes (op.mode) */
   VP_STATS_MEAN_STD_CLAMP = 1,     /* [mean ; sqrt(clamp(sum((x-mean)^2)/R, eps))]                (pooling.py:91-94,108) */
   VP_STATS_MEAN_STD_UNBIASED = 2,  /* [mean ; sqrt(sum((x-mean)^2)/(R-1))]                        (campplus.py:27-33) */
   VP_STATS_MEAN_STD_TSTP = 3,      /* [mean ; sqrt(sum((x-mean)^2)/(R-1) + eps)]                  (pooling.py:140-148) */
-  VP_STATS_SEG_CONTEXT = 4         /* out[b, s, c] = mean over rows + mean over segment s (ceil)  (campplus.py:96-111) */
+  VP_STATS_SEG_CONTEXT = 4,        /* out[b, s, c] = mean over rows + mean over segment s (ceil)  (campplus.py:96-111) */
+  VP_STATS_MEAN_VAR_UNBIASED = 5   /* [mean ; sum((x-mean)^2)/(R-1)]  (TemporalStatisticsPooling returns the VARIANCE, pooling.py:44-46) */
 };
 enum { VP_EW_GATE_RES = 0, VP_EW_AFF = 1, VP_EW_COPY = 2 };
 enum { VP_BUF_NONE = -1, VP_BUF_INPUT = -2, VP_BUF_OUTPUT = -3 };  /* special values for activation offsets */

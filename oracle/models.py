@@ -68,6 +68,39 @@ def asp_pool(sd, p, x, eps=1e-12):
     return torch.cat((mean, std), dim=1)
 
 
+def pool_forward(sd, p, kind, x):
+    """pooling.py: ASP (:68-127), SAP (:50-65), TAP (:8-26), TSP (:29-47, returns the VARIANCE)."""
+    if kind == 'ASP':
+        return asp_pool(sd, p, x)
+    if kind == 'SAP':
+        a = torch.tanh(F.conv1d(x, sd[p + '.linear1.weight'], sd[p + '.linear1.bias']))
+        a = torch.softmax(F.conv1d(a, sd[p + '.linear2.weight'], sd[p + '.linear2.bias']), dim=2)
+        return torch.sum(a * x, dim=2)
+    if kind == 'TAP':
+        return torch.mean(x, dim=2).flatten(start_dim=1)
+    if kind == 'TSP':
+        return torch.cat((torch.mean(x, dim=2), torch.var(x, dim=2)), dim=1)
+    raise Exception(f'没有{kind}池化层！')
+
+
+def _pool_shapes(d, p, kind, c, att=128):
+    """Parameters of the pooling module and the width of its output."""
+    if kind == 'ASP':
+        _asp_shapes(d, p, c, att)
+        return 2 * c
+    if kind == 'SAP':
+        d[p + '.linear1.weight'] = (128, c, 1)
+        d[p + '.linear1.bias'] = (128,)
+        d[p + '.linear2.weight'] = (c, 128, 1)
+        d[p + '.linear2.bias'] = (c,)
+        return c
+    if kind == 'TAP':
+        return c
+    if kind == 'TSP':
+        return 2 * c
+    raise Exception(f'没有{kind}池化层！')
+
+
 def _asp_shapes(d, p, c, att=128):
     _tdnn_block_shapes(d, p + '.tdnn', c * 3, att, 1)
     d[p + '.conv.conv.weight'] = (c, att, 1)
@@ -80,7 +113,7 @@ def _asp_shapes(d, p, c, att=128):
 def ecapa_param_shapes(input_size, embd_dim=192, pooling_type='ASP', channels=(512, 512, 512, 512, 1536),
                        kernel_sizes=(5, 3, 3, 3, 1), dilations=(1, 2, 3, 4, 1), attention_channels=128,
                        res2net_scale=8, se_channels=128, global_context=True):
-    assert pooling_type == 'ASP' and global_context
+    assert global_context
     d = OrderedDict()
     _tdnn_block_shapes(d, 'blocks.0', input_size, channels[0], kernel_sizes[0])
     for i in range(1, len(channels) - 1):
@@ -99,9 +132,9 @@ def ecapa_param_shapes(input_size, embd_dim=192, pooling_type='ASP', channels=(5
             d[p + '.shortcut.conv.weight'] = (c, cin, 1)
             d[p + '.shortcut.conv.bias'] = (c,)
     _tdnn_block_shapes(d, 'mfa', channels[-1], channels[-1], kernel_sizes[-1])
-    _asp_shapes(d, 'asp', channels[-1], attention_channels)
-    _bn_shapes(d, 'asp_bn.norm', channels[-1] * 2)
-    d['fc.conv.weight'] = (embd_dim, channels[-1] * 2, 1)
+    width = _pool_shapes(d, 'asp', pooling_type, channels[-1], attention_channels)
+    _bn_shapes(d, 'asp_bn.norm' if pooling_type == 'ASP' else 'asp_bn', width)     # ecapa_tdnn.py:224 vs :232,239,246
+    d['fc.conv.weight'] = (embd_dim, width, 1)
     d['fc.conv.bias'] = (embd_dim,)
     return d
 
@@ -134,8 +167,8 @@ def ecapa_forward(sd, x, embd_dim=192, pooling_type='ASP', channels=(512, 512, 5
         x = s * h + res
         outs.append(x)
     x = _tdnn_block(sd, 'mfa', torch.cat(outs, dim=1), dilations[-1])          # ecapa_tdnn.py:273-274
-    x = asp_pool(sd, 'asp', x)
-    x = _bn(sd, 'asp_bn.norm', x)
+    x = pool_forward(sd, 'asp', pooling_type, x)
+    x = _bn(sd, 'asp_bn.norm' if pooling_type == 'ASP' else 'asp_bn', x)
     return _same_conv1d(sd, 'fc', x.unsqueeze(2)).squeeze(-1)                  # ecapa_tdnn.py:279-281
 
 
@@ -143,7 +176,6 @@ def ecapa_forward(sd, x, embd_dim=192, pooling_type='ASP', channels=(512, 512, 5
 # TDNN (tdnn.py:9-68), pooling_type 'ASP'
 # ---------------------------------------------------------------------------------------------
 def tdnn_param_shapes(input_size, channels=512, embd_dim=192, pooling_type='ASP'):
-    assert pooling_type == 'ASP'
     d = OrderedDict()
     ks = (5, 3, 3, 1, 1)
     for i, k in enumerate(ks, start=1):
@@ -151,9 +183,9 @@ def tdnn_param_shapes(input_size, channels=512, embd_dim=192, pooling_type='ASP'
         d[f'td_layer{i}.bias'] = (channels,)
         if i < 5:
             _bn_shapes(d, f'bn{i}', channels)
-    _asp_shapes(d, 'pooling', channels, 128)
-    _bn_shapes(d, 'bn5', channels * 2)
-    d['linear.weight'] = (embd_dim, channels * 2)
+    width = _pool_shapes(d, 'pooling', pooling_type, channels, 128)
+    _bn_shapes(d, 'bn5', width)
+    d['linear.weight'] = (embd_dim, width)
     d['linear.bias'] = (embd_dim,)
     _bn_shapes(d, 'bn6', embd_dim)
     return d
@@ -165,7 +197,7 @@ def tdnn_forward(sd, x, channels=512, embd_dim=192, pooling_type='ASP'):
         x = F.relu(F.conv1d(x, sd[f'td_layer{i}.weight'], sd[f'td_layer{i}.bias'], dilation=dil))
         if i < 5:
             x = _bn(sd, f'bn{i}', x)
-    x = _bn(sd, 'bn5', asp_pool(sd, 'pooling', x))
+    x = _bn(sd, 'bn5', pool_forward(sd, 'pooling', pooling_type, x))
     return _bn(sd, 'bn6', F.linear(x, sd['linear.weight'], sd['linear.bias']))
 
 
@@ -271,7 +303,6 @@ def campplus_forward(sd, x, embd_dim=512, growth_rate=32, bn_size=4, init_channe
 # ---------------------------------------------------------------------------------------------
 def resnetse_param_shapes(input_size, layers=(3, 4, 6, 3), num_filters=(32, 64, 128, 256), embd_dim=192,
                           pooling_type='ASP'):
-    assert pooling_type == 'ASP'
     d = OrderedDict()
     d['conv1.weight'] = (num_filters[0], 1, 3, 3)
     _bn_shapes(d, 'bn1', num_filters[0])
@@ -295,9 +326,9 @@ def resnetse_param_shapes(input_size, layers=(3, 4, 6, 3), num_filters=(32, 64, 
                 _bn_shapes(d, p + '.downsample.1', planes * 2)
             inpl = planes * 2
     cat = num_filters[3] * 2 * (input_size // 8)
-    _asp_shapes(d, 'pooling', cat, 128)
-    _bn_shapes(d, 'bn2', cat * 2)
-    d['linear.weight'] = (embd_dim, cat * 2)
+    width = _pool_shapes(d, 'pooling', pooling_type, cat, 128)
+    _bn_shapes(d, 'bn2', width)
+    d['linear.weight'] = (embd_dim, width)
     d['linear.bias'] = (embd_dim,)
     _bn_shapes(d, 'bn3', embd_dim)
     return d
@@ -323,7 +354,7 @@ def resnetse_forward(sd, x, layers=(3, 4, 6, 3), num_filters=(32, 64, 128, 256),
                 res = _bn(sd, p + '.downsample.1', F.conv2d(x, sd[p + '.downsample.0.weight'], stride=stride))
             x = F.relu(out + res)
     x = x.reshape(x.shape[0], -1, x.shape[-1])                                  # resnet_se.py:139
-    x = _bn(sd, 'bn2', asp_pool(sd, 'pooling', x))
+    x = _bn(sd, 'bn2', pool_forward(sd, 'pooling', pooling_type, x))
     return _bn(sd, 'bn3', F.linear(x, sd['linear.weight'], sd['linear.bias']))
 
 

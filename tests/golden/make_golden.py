@@ -93,6 +93,11 @@ CASES = {
                                         pooling_type='ASP'), MEL16, [16000, 11000]),
     'eres2net_small': ('ERes2Net', dict(embd_dim=32, num_blocks=[1, 1, 2, 1], m_channels=8), FBANK24,
                        [14400, 9000]),
+    'ecapa_sap_small': ('EcapaTdnn', dict(embd_dim=32, pooling_type='SAP', channels=[64, 64, 64, 64, 192],
+                                          res2net_scale=4, se_channels=16), FBANK80, [9000, 6400]),
+    'tdnn_tsp_small': ('TDNN', dict(embd_dim=32, channels=64, pooling_type='TSP'), FBANK24, [9600, 8000]),
+    'resnetse_tap_small': ('ResNetSE', dict(embd_dim=32, layers=[1, 1, 1, 1], num_filters=[16, 16, 32, 32],
+                                            pooling_type='TAP'), MEL16, [12000, 11000]),
     'eres2net_wide_small': ('ERes2Net', dict(embd_dim=32, num_blocks=[1, 1, 1, 1], m_channels=8, mul_channel=2,
                                              expansion=4, base_width=32, scale=3), FBANK24, [12000]),
 }

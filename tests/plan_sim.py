@@ -134,6 +134,8 @@ class Sim:
             sd = np.sqrt(np.maximum(ssq / R, o.eps))
         elif o.mode == L.STATS_MEAN_STD_UNBIASED:
             sd = np.sqrt(ssq / (R - 1))
+        elif o.mode == L.STATS_MEAN_VAR_UNBIASED:
+            sd = ssq / (R - 1)
         else:
             sd = np.sqrt(ssq / (R - 1) + o.eps)
         self.wr(o.dst, o.B, o.out_ld, o.out_coff, 2 * o.Cin, np.concatenate([mean, sd], 1))
@@ -145,6 +147,9 @@ class Sim:
         e = np.exp(Lg - Lg.max(1, keepdims=True))
         a = e / e.sum(1, keepdims=True)
         mean = (a * X).sum(1)
+        if o.mode == 1:
+            self.wr(o.dst, o.B, o.out_ld, o.out_coff, Cn, mean)
+            return
         sd = np.sqrt(np.maximum((a * (X - mean[:, None]) ** 2).sum(1), o.eps))
         self.wr(o.dst, o.B, o.out_ld, o.out_coff, 2 * Cn, np.concatenate([mean, sd], 1))
 

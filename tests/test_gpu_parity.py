@@ -100,7 +100,8 @@ def test_frontend_loud_errors():
 
 
 # ------------------------------------------------------------------------------------------------ backbones
-SMALL = ['ecapa_small', 'tdnn_small', 'campplus_small', 'resnetse_small', 'eres2net_small', 'eres2net_wide_small']
+SMALL = ['ecapa_small', 'tdnn_small', 'campplus_small', 'resnetse_small', 'eres2net_small', 'eres2net_wide_small',
+         'ecapa_sap_small', 'tdnn_tsp_small', 'resnetse_tap_small']
 
 
 @pytest.mark.parametrize('name', SMALL)

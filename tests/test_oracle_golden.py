@@ -10,7 +10,8 @@ from conftest import load_golden, rel_l2
 from oracle import frontend as fe
 from oracle import models as om
 
-SMALL = ['ecapa_small', 'tdnn_small', 'campplus_small', 'resnetse_small', 'eres2net_small', 'eres2net_wide_small']
+SMALL = ['ecapa_small', 'tdnn_small', 'campplus_small', 'resnetse_small', 'eres2net_small', 'eres2net_wide_small',
+         'ecapa_sap_small', 'tdnn_tsp_small', 'resnetse_tap_small']
 
 
 @pytest.mark.parametrize('name', SMALL)

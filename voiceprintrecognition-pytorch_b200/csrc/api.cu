@@ -284,8 +284,8 @@ static int validate_op(vp_program* p, const vp_op& o, int i) {
     case VP_OP_COLSTATS: {
       const long long R = (long long)o.Tin * o.Fin;
       if (R < 1 || o.Cin < 1) return fail(h, VP_ERR_INVALID, "op %d: stats geometry", i);
-      if (o.mode < VP_STATS_MEAN || o.mode > VP_STATS_SEG_CONTEXT) return fail(h, VP_ERR_INVALID, "op %d: stats mode", i);
-      if ((o.mode == VP_STATS_MEAN_STD_UNBIASED || o.mode == VP_STATS_MEAN_STD_TSTP) && R < 2)
+      if (o.mode < VP_STATS_MEAN || o.mode > VP_STATS_MEAN_VAR_UNBIASED) return fail(h, VP_ERR_INVALID, "op %d: stats mode", i);
+      if ((o.mode == VP_STATS_MEAN_STD_UNBIASED || o.mode == VP_STATS_MEAN_STD_TSTP || o.mode == VP_STATS_MEAN_VAR_UNBIASED) && R < 2)
         return fail(h, VP_ERR_INVALID, "op %d: unbiased std needs >= 2 rows", i);
       TRY(check_act_buf(p, "src", o.src, view_floats((long long)o.B * R, o.in_ld, o.in_coff, o.Cin), false, i));
       if (o.mode == VP_STATS_SEG_CONTEXT) {
@@ -303,7 +303,8 @@ static int validate_op(vp_program* p, const vp_op& o, int i) {
       const long long rows = (long long)o.B * o.Tin;
       TRY(check_act_buf(p, "x", o.src, view_floats(rows, o.in_ld, o.in_coff, o.Cin), false, i));
       TRY(check_act_buf(p, "logits", o.src2, view_floats(rows, o.src2_ld, o.src2_coff, o.Cin), false, i));
-      TRY(check_act_buf(p, "dst", o.dst, view_floats(o.B, o.out_ld, o.out_coff, 2 * o.Cin), true, i));
+      if (o.mode != 0 && o.mode != 1) return fail(h, VP_ERR_INVALID, "op %d: asp mode", i);
+      TRY(check_act_buf(p, "dst", o.dst, view_floats(o.B, o.out_ld, o.out_coff, (o.mode == 1 ? 1 : 2) * o.Cin), true, i));
       return VP_OK;
     }
     case VP_OP_EW: {
@@ -442,7 +443,7 @@ static int run_ops(vp_program* p, const float* feats, float* emb, cudaStream_t s
         a.x = rd(p, o.src, feats, emb); a.logit = rd(p, o.src2, feats, emb);
         a.dst = const_cast<float*>(rd(p, o.dst, feats, emb));
         a.B = o.B; a.T = o.Tin; a.C = o.Cin; a.x_ld = o.in_ld; a.x_coff = o.in_coff; a.l_ld = o.src2_ld;
-        a.l_coff = o.src2_coff; a.out_ld = o.out_ld; a.out_coff = o.out_coff; a.eps = o.eps;
+        a.l_coff = o.src2_coff; a.out_ld = o.out_ld; a.out_coff = o.out_coff; a.eps = o.eps; a.mean_only = o.mode == 1;
         CUDA_TRY(h, launch_asp_pool(a, st));
         break;
       }

@@ -21,7 +21,7 @@ struct StatsParams {
 // x: [B,T,C] view (x_ld/x_coff), logits likewise; dst[b, c] = mean, dst[b, C + c] = std.
 struct AspParams {
   const float* x; const float* logit; float* dst;
-  int B, T, C, x_ld, x_coff, l_ld, l_coff, out_ld, out_coff;
+  int B, T, C, x_ld, x_coff, l_ld, l_coff, out_ld, out_coff, mean_only;
   float eps;
 };
 

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(256) colstats_kernel(const __grid_constant__ S
   if (wid == 0 && ok) {
     float sd;
     if (p.mode == VP_STATS_MEAN_STD_CLAMP) sd = sqrtf(fmaxf(ssq / (float)p.R, p.eps));
+    else if (p.mode == VP_STATS_MEAN_VAR_UNBIASED) sd = ssq / (float)(p.R - 1);
     else if (p.mode == VP_STATS_MEAN_STD_UNBIASED) sd = sqrtf(ssq / (float)(p.R - 1));
     else sd = sqrtf(ssq / (float)(p.R - 1) + p.eps);
     o[c] = mean;
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(256) asp_pool_kernel(const __grid_constant__ A
   if (wid == 0 && ok) {
     float* o = p.dst + (size_t)b * p.out_ld + p.out_coff;
     o[c] = mean;
-    o[p.C + c] = sqrtf(fmaxf(sq / se, p.eps));
+    if (!p.mean_only) o[p.C + c] = sqrtf(fmaxf(sq / se, p.eps));
   }
 }
 
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(256) asp_pool_smem_kernel(const __grid_constan
   if (wid == 0 && ok) {
     float* o = p.dst + (size_t)b * p.out_ld + p.out_coff;
     o[c] = mean;
-    o[p.C + c] = sqrtf(fmaxf(sq / se, p.eps));
+    if (!p.mean_only) o[p.C + c] = sqrtf(fmaxf(sq / se, p.eps));
   }
 }
 

@@ -12,6 +12,7 @@ ACT_NONE, ACT_RELU, ACT_HARDTANH20, ACT_SIGMOID, ACT_TANH, ACT_SILU = 0, 1, 2, 3
 PAD_ZERO, PAD_REFLECT = 0, 1
 SRC2_NONE, SRC2_ADD, SRC2_CONCAT = 0, 1, 2
 STATS_MEAN, STATS_MEAN_STD_CLAMP, STATS_MEAN_STD_UNBIASED, STATS_MEAN_STD_TSTP, STATS_SEG_CONTEXT = 0, 1, 2, 3, 4
+STATS_MEAN_VAR_UNBIASED = 5
 EW_GATE_RES, EW_AFF, EW_COPY = 0, 1, 2
 BUF_NONE, BUF_INPUT, BUF_OUTPUT = -1, -2, -3
 ENGINE_AUTO, ENGINE_FFMA, ENGINE_TC = 0, 1, 2

@@ -285,8 +285,9 @@ class PlanBuilder:
         self.ops.append(o)
         return o
 
-    def asp_pool(self, x, logits, dst, T, eps=1e-12):
+    def asp_pool(self, x, logits, dst, T, eps=1e-12, mean_only=False):
         o = self._new(L.OP_ASP_POOL)
+        o.mode = 1 if mean_only else 0
         o.src, o.in_ld, o.in_coff, o.Cin = x.off, x.ld, x.coff, x.C
         o.src2, o.src2_ld, o.src2_coff = logits.off, logits.ld, logits.coff
         o.dst, o.out_ld, o.out_coff = dst.off, dst.ld, dst.coff

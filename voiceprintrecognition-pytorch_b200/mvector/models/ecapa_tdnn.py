@@ -13,7 +13,7 @@ import numpy as np
 
 from .. import _lib as L
 from .base import Backbone, _np64, bn_affine
-from .pooling import asp_shapes, lower_asp, pack_asp
+from .pooling import check_pooling_type, lower_pool, pack_pool, pool_shapes, pool_width
 
 
 def _tdnn_block_shapes(d, p, cin, cout, k):
@@ -37,10 +37,8 @@ class EcapaTdnn(Backbone):
                  groups=[1, 1, 1, 1, 1]):
         super().__init__()
         assert len(channels) == len(kernel_sizes) and len(channels) == len(dilations)
-        if pooling_type != 'ASP':
-            if pooling_type in ('SAP', 'TAP', 'TSP'):
-                raise NotImplementedError(f'pooling_type {pooling_type} is not lowered yet (SURVEY.md 8f)')
-            raise Exception(f'没有{pooling_type}池化层！')
+        check_pooling_type(pooling_type)
+        self.pooling_type = pooling_type
         if activation is not None or not global_context or any(g != 1 for g in groups):
             raise NotImplementedError('EcapaTdnn: only ReLU / global_context=True / groups=1 are lowered')
         for c in channels[:-1]:
@@ -71,11 +69,12 @@ class EcapaTdnn(Backbone):
                 d[p + '.shortcut.conv.weight'] = (c, cin, 1)
                 d[p + '.shortcut.conv.bias'] = (c,)
         _tdnn_block_shapes(d, 'mfa', ch[-1], ch[-1], ks[-1])
-        asp_shapes(d, 'asp', ch[-1], self.attention_channels)
+        width = pool_shapes(d, 'asp', self.pooling_type, ch[-1], self.attention_channels)
+        bn = 'asp_bn.norm' if self.pooling_type == 'ASP' else 'asp_bn'          # ecapa_tdnn.py:224 vs :232,239,246
         for n in ('weight', 'bias', 'running_mean', 'running_var'):
-            d['asp_bn.norm.' + n] = (ch[-1] * 2,)
-        d['asp_bn.norm.num_batches_tracked'] = ()
-        d['fc.conv.weight'] = (self.embd_dim, ch[-1] * 2, 1)
+            d[f'{bn}.{n}'] = (width,)
+        d[bn + '.num_batches_tracked'] = ()
+        d['fc.conv.weight'] = (self.embd_dim, width, 1)
         d['fc.conv.bias'] = (self.embd_dim,)
         return d
 
@@ -105,9 +104,9 @@ class EcapaTdnn(Backbone):
                 blk['sc_b'] = arena.add(p + '.sc.b', sd[p + '.shortcut.conv.bias'])
             o[p] = blk
         o['mfa'] = self._pack_tdnn_block(sd, 'mfa', arena)
-        o['asp'] = pack_asp(sd, 'asp', arena, ch[-1])
-        # asp_bn -> fc (ecapa_tdnn.py:278-281) is affine-then-linear: fold into one [embd, 2C] product (fp64 fold)
-        s, h = bn_affine(sd, 'asp_bn.norm')
+        o['asp'] = pack_pool(sd, 'asp', self.pooling_type, arena, ch[-1])
+        # asp_bn -> fc (ecapa_tdnn.py:278-281) is affine-then-linear: fold into one [embd, width] product (fp64 fold)
+        s, h = bn_affine(sd, 'asp_bn.norm' if self.pooling_type == 'ASP' else 'asp_bn')
         W = _np64(sd['fc.conv.weight'])[:, :, 0]
         o['fc_w'] = arena.add('fc.w', W * s[None, :])
         o['fc_b'] = arena.add('fc.b', W @ h + _np64(sd['fc.conv.bias']))
@@ -171,8 +170,9 @@ class EcapaTdnn(Backbone):
         self._tdnn_block(pb, cat, xm, o['mfa'], T, ks[-1], dl[-1])
         pb.free(cat)
         pb.tap('mfa', xm, M)
-        pooled = pb.alloc(B, 2 * ch[-1])
-        lower_asp(pb, o['asp'], xm, B, T, pooled)
+        width = pool_width(self.pooling_type, ch[-1])
+        pooled = pb.alloc(B, width)
+        lower_pool(pb, o['asp'], self.pooling_type, xm, B, T, pooled)
         pb.tap('pooled', pooled, B)
-        pb.conv(pooled, pb.output_view(self.embd_dim, B), o['fc_w'], 2 * ch[-1], 1, 1, bias=o['fc_b'],
+        pb.conv(pooled, pb.output_view(self.embd_dim, B), o['fc_w'], width, 1, 1, bias=o['fc_b'],
                 engine=L.ENGINE_FFMA)

@@ -56,3 +56,73 @@ def lower_asp(pb, o, x, B, T, pooled):
     pb.asp_pool(x, logits, pooled, T, eps=1e-12)
     for v in (logits, h, ub, stats):
         pb.free(v)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The other pooling types of the reference (pooling.py:8-65), selectable through ``pooling_type`` in the yml:
+#   TAP  mean over T                         -> one COLSTATS(MEAN)
+#   TSP  mean ; unbiased VARIANCE            -> one COLSTATS(MEAN_VAR_UNBIASED)   (pooling.py:44-46 returns var, not std)
+#   SAP  softmax_T(W2 tanh(W1 x + b1) + b2)-weighted mean -> two CONVs + ASP_POOL(mean only)
+# ---------------------------------------------------------------------------------------------------------------
+POOL_TYPES = ('ASP', 'SAP', 'TAP', 'TSP')
+
+
+def check_pooling_type(pooling_type):
+    if pooling_type not in POOL_TYPES:
+        raise Exception(f'没有{pooling_type}池化层！')
+
+
+def pool_width(kind, c):
+    return 2 * c if kind in ('ASP', 'TSP') else c
+
+
+def pool_shapes(d, p, kind, c, att=128):
+    if kind == 'ASP':
+        asp_shapes(d, p, c, att)
+    elif kind == 'SAP':
+        d[p + '.linear1.weight'] = (128, c, 1)
+        d[p + '.linear1.bias'] = (128,)
+        d[p + '.linear2.weight'] = (c, 128, 1)
+        d[p + '.linear2.bias'] = (c,)
+    return pool_width(kind, c)
+
+
+def pack_pool(sd, p, kind, arena, C, perm=None):
+    if kind == 'ASP':
+        return pack_asp(sd, p, arena, C, perm)
+    if kind == 'SAP':
+        W1 = _np64(sd[p + '.linear1.weight'])[:, :, 0]          # [128, C]
+        W2 = _np64(sd[p + '.linear2.weight'])[:, :, 0]          # [C, 128]
+        b2 = _np64(sd[p + '.linear2.bias'])
+        if perm is not None:
+            W1, W2, b2 = W1[:, perm], W2[perm], b2[perm]
+        return dict(C=C, A=W1.shape[0], w1=arena.add_conv(p + '.w1', W1), b1=arena.add(p + '.b1', sd[p + '.linear1.bias']),
+                    w2=arena.add_conv(p + '.w2', W2), b2=arena.add(p + '.b2', b2))
+    return dict(C=C)
+
+
+def pool_perm(kind, C, perm):
+    """Column permutation of the pooled vector when the backbone's channel order is permuted (2-D nets)."""
+    if perm is None:
+        return None
+    return np.concatenate([perm, C + perm]) if kind in ('ASP', 'TSP') else perm
+
+
+def lower_pool(pb, o, kind, x, B, T, pooled):
+    if kind == 'ASP':
+        lower_asp(pb, o, x, B, T, pooled)
+    elif kind == 'TAP':
+        pb.colstats(x, pooled, T, L.STATS_MEAN)
+    elif kind == 'TSP':
+        if T < 2:
+            raise ValueError('TSP pooling needs at least 2 frames (unbiased variance)')
+        pb.colstats(x, pooled, T, L.STATS_MEAN_VAR_UNBIASED)
+    elif kind == 'SAP':
+        C, A = o['C'], o['A']
+        h = pb.alloc(B * T, A)
+        pb.conv(x, h, o['w1'], C, T, T, bias=o['b1'], act=L.ACT_TANH)
+        logits = pb.alloc(B * T, C)
+        pb.conv(h, logits, o['w2'], A, T, T, bias=o['b2'])
+        pb.asp_pool(x, logits, pooled, T, mean_only=True)
+        pb.free(logits)
+        pb.free(h)

@@ -14,17 +14,15 @@ from ..engine import View
 from .base import Backbone, _np64, bn_affine
 from .campplus import L_view1
 from .conv2d_util import bn_names, fc_perm, fold_conv_bn, out_len
-from .pooling import asp_shapes, lower_asp, pack_asp
+from .pooling import check_pooling_type, lower_pool, pack_pool, pool_perm, pool_shapes, pool_width
 
 
 class ResNetSE(Backbone):
     def __init__(self, input_size, layers=[3, 4, 6, 3], num_filters=[32, 64, 128, 256], embd_dim=192,
                  pooling_type='ASP'):
         super().__init__()
-        if pooling_type != 'ASP':
-            if pooling_type in ('SAP', 'TAP', 'TSP'):
-                raise NotImplementedError(f'pooling_type {pooling_type} is not lowered yet (SURVEY.md 8f)')
-            raise Exception(f'没有{pooling_type}池化层！')
+        check_pooling_type(pooling_type)
+        self.pooling_type = pooling_type
         self.input_size, self.embd_dim = input_size, embd_dim
         self.layers, self.nf = list(layers), list(num_filters)
         self.F8 = input_size // 8
@@ -57,9 +55,9 @@ class ResNetSE(Backbone):
             if ds:
                 d[p + '.downsample.0.weight'] = (planes * 2, inpl, 1, 1)
                 bn_names(d, p + '.downsample.1', planes * 2)
-        asp_shapes(d, 'pooling', self.cat, 128)
-        bn_names(d, 'bn2', self.cat * 2)
-        d['linear.weight'] = (self.embd_dim, self.cat * 2)
+        width = pool_shapes(d, 'pooling', self.pooling_type, self.cat, 128)
+        bn_names(d, 'bn2', width)
+        d['linear.weight'] = (self.embd_dim, width)
         d['linear.bias'] = (self.embd_dim,)
         bn_names(d, 'bn3', self.embd_dim)
         return d
@@ -84,14 +82,13 @@ class ResNetSE(Backbone):
                                 b2=arena.add(p + '.se.b2', sd[p + '.se.fc.2.bias']))
         C4 = self.nf[3] * 2
         perm = fc_perm(self.F8, C4)
-        o['asp'] = pack_asp(sd, 'pooling', arena, self.cat, perm=perm)
+        o['asp'] = pack_pool(sd, 'pooling', self.pooling_type, arena, self.cat, perm=perm)
         s2, h2 = bn_affine(sd, 'bn2')
         s3, h3 = bn_affine(sd, 'bn3')
         W, b = _np64(sd['linear.weight']), _np64(sd['linear.bias'])
         Wf = s3[:, None] * W * s2[None, :]
         bf = s3 * (W @ h2 + b) + h3
-        perm2 = np.concatenate([perm, self.cat + perm])
-        o['fc_w'] = arena.add('fc.w', Wf[:, perm2])
+        o['fc_w'] = arena.add('fc.w', Wf[:, pool_perm(self.pooling_type, self.cat, perm)])
         o['fc_b'] = arena.add('fc.b', bf)
 
     def _lower(self, pb, B, T):
@@ -137,8 +134,9 @@ class ResNetSE(Backbone):
         assert f == self.F8, 'input_size must be a multiple of 8'
         C4 = self.nf[3] * 2
         flat = View(x.off, f * C4, 0, f * C4)
-        pooled = pb.alloc(B, 2 * self.cat)
-        lower_asp(pb, o['asp'], flat, B, t, pooled)
+        width = pool_width(self.pooling_type, self.cat)
+        pooled = pb.alloc(B, width)
+        lower_pool(pb, o['asp'], self.pooling_type, flat, B, t, pooled)
         pb.free(x)
-        pb.conv(pooled, pb.output_view(self.embd_dim, B), o['fc_w'], 2 * self.cat, 1, 1, bias=o['fc_b'],
+        pb.conv(pooled, pb.output_view(self.embd_dim, B), o['fc_w'], width, 1, 1, bias=o['fc_b'],
                 engine=L.ENGINE_FFMA)

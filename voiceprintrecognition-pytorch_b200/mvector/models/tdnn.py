@@ -7,7 +7,7 @@ import numpy as np
 from .. import _lib as L
 from .base import Backbone, _np64, bn_affine
 from .ecapa_tdnn import conv1d_weight
-from .pooling import asp_shapes, lower_asp, pack_asp
+from .pooling import check_pooling_type, lower_pool, pack_pool, pool_shapes, pool_width
 
 _KS = (5, 3, 3, 1, 1)
 _DIL = (1, 2, 3, 1, 1)
@@ -16,10 +16,8 @@ _DIL = (1, 2, 3, 1, 1)
 class TDNN(Backbone):
     def __init__(self, input_size, channels=512, embd_dim=192, pooling_type='ASP'):
         super().__init__()
-        if pooling_type != 'ASP':
-            if pooling_type in ('SAP', 'TAP', 'TSP'):
-                raise NotImplementedError(f'pooling_type {pooling_type} is not lowered yet (SURVEY.md 8f)')
-            raise Exception(f'没有{pooling_type}池化层！')
+        check_pooling_type(pooling_type)
+        self.pooling_type = pooling_type
         self.input_size, self.channels, self.embd_dim = input_size, channels, embd_dim
 
     def param_shapes(self):
@@ -32,12 +30,12 @@ class TDNN(Backbone):
                 for n in ('weight', 'bias', 'running_mean', 'running_var'):
                     d[f'bn{i}.{n}'] = (c,)
                 d[f'bn{i}.num_batches_tracked'] = ()
-        asp_shapes(d, 'pooling', c, 128)
-        for nm, n_ in (('bn5', c * 2),):
+        width = pool_shapes(d, 'pooling', self.pooling_type, c, 128)
+        for nm, n_ in (('bn5', width),):
             for n in ('weight', 'bias', 'running_mean', 'running_var'):
                 d[f'{nm}.{n}'] = (n_,)
             d[f'{nm}.num_batches_tracked'] = ()
-        d['linear.weight'] = (self.embd_dim, c * 2)
+        d['linear.weight'] = (self.embd_dim, width)
         d['linear.bias'] = (self.embd_dim,)
         for n in ('weight', 'bias', 'running_mean', 'running_var'):
             d[f'bn6.{n}'] = (self.embd_dim,)
@@ -53,7 +51,7 @@ class TDNN(Backbone):
                 s, h = bn_affine(sd, f'bn{i}')
                 e['s'], e['h'] = arena.add(f'bn{i}.s', s), arena.add(f'bn{i}.h', h)
             o[f'td{i}'] = e
-        o['asp'] = pack_asp(sd, 'pooling', arena, self.channels)
+        o['asp'] = pack_pool(sd, 'pooling', self.pooling_type, arena, self.channels)
         s5, h5 = bn_affine(sd, 'bn5')
         s6, h6 = bn_affine(sd, 'bn6')
         W, b = _np64(sd['linear.weight']), _np64(sd['linear.bias'])
@@ -75,7 +73,8 @@ class TDNN(Backbone):
             if i > 1:
                 pb.free(x)
             x, t = y, tout
-        pooled = pb.alloc(B, 2 * c)
-        lower_asp(pb, o['asp'], x, B, t, pooled)
+        width = pool_width(self.pooling_type, c)
+        pooled = pb.alloc(B, width)
+        lower_pool(pb, o['asp'], self.pooling_type, x, B, t, pooled)
         pb.free(x)
-        pb.conv(pooled, pb.output_view(self.embd_dim, B), o['fc_w'], 2 * c, 1, 1, bias=o['fc_b'], engine=L.ENGINE_FFMA)
+        pb.conv(pooled, pb.output_view(self.embd_dim, B), o['fc_w'], width, 1, 1, bias=o['fc_b'], engine=L.ENGINE_FFMA)
