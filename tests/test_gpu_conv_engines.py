@@ -89,7 +89,7 @@ CASES = dict(
     cam_local_gate_seg=dict(seed=11, B=6, Tin=249, Tout=249, Cin=128, N=32, KT=3, dT=2, padT=2, gate=True, seg_len=100, n_seg=3),
     k5_stride2_zero=dict(seed=12, B=8, Tin=298, Tout=149, Cin=320, N=128, KT=5, sT=2, padT=2, bias=True, act=1),
     n_tail_192=dict(seed=13, B=3, Tin=400, Tout=400, Cin=96, N=192, bias=True),
-    long_k_chunked_9216=dict(seed=15, B=2, Tin=40, Fin=20, Tout=20, Fout=10, Cin=1024, N=256, KT=3, KF=3, sT=2, sF=2, padT=1, padF=1),
+    long_k_chunked_9216=dict(seed=15, B=6, Tin=40, Fin=20, Tout=20, Fout=10, Cin=1024, N=256, KT=3, KF=3, sT=2, sF=2, padT=1, padF=1),
     long_k_chunked_4096_n128=dict(seed=16, B=7, Tin=151, Tout=151, Cin=4096, N=128, ubias=True, act=1, post=True, act2=4),
     k_tail_72=dict(seed=14, B=11, Tin=100, Tout=100, Cin=24, N=24, KT=3, padT=1, bias=True, act=2),
 )

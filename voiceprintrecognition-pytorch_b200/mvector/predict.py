@@ -173,8 +173,9 @@ class MVectorPredictor:
             audio_segment.normalize(target_db=ds.target_dB)
         return audio_segment
 
-    #: utterances per pipeline chunk of predict_batch (host gather + H2D of chunk k+1 overlap the kernels of chunk k)
-    CHUNK = int(os.environ.get('VPB_PREDICT_CHUNK', '128'))
+    #: utterances per compute chunk (one fused vp_embed_wave call each) and per host-gather / H2D slice
+    CHUNK = int(os.environ.get('VPB_PREDICT_CHUNK', '256'))
+    COPY_SLICE = int(os.environ.get('VPB_COPY_SLICE', '64'))
     GATHER_THREADS = int(os.environ.get('VPB_GATHER_THREADS', '8'))
 
     def _pinned_slot(self, slot, n):
@@ -189,10 +190,11 @@ class MVectorPredictor:
         """waves: list of 1-D float32 arrays (already loaded / resampled / normalised) -> np.float32 [B, embd_dim].
 
         Reference semantics (predict.py:244-262): every utterance is zero padded to the longest item of the WHOLE list,
-        T and the CMN mean follow that padded length, frames >= round(len/Lmax * T) are zeroed.  Because every op is
-        per-utterance, the list is processed in chunks of CHUNK utterances: while the GPU runs the fused
-        ``vp_embed_wave`` of chunk k, the host gathers chunk k+1 into pinned memory and its H2D copy runs on a second
-        stream.  One D2H of the [B, embd] result at the end."""
+        T and the CMN mean follow that padded length, frames >= round(len/Lmax * T) are zeroed.  Host side: the list is
+        gathered into pinned memory in slices of COPY_SLICE utterances by a native multi-threaded copy and each slice's
+        H2D transfer is enqueued on a copy stream while the next slice is gathered; the kernels then run over compute
+        chunks of CHUNK utterances (measured on B200: splitting 256 utterances into smaller compute chunks costs more
+        GPU efficiency than the overlap buys).  One D2H of the [B, embd] result at the end."""
         from . import _lib as L
         B = len(waves)
         fz = self._audio_featurizer
@@ -208,45 +210,41 @@ class MVectorPredictor:
         D = self.predictor.embd_dim
         emb = torch.empty(B, D, dtype=torch.float32, device=dev)
         cb = min(self.CHUNK, B)
-        # chunk schedule: a short first chunk gets the GPU busy early (its host gather + H2D are the only exposed copies),
-        # then full chunks; [cb/4, 3cb/4, cb, cb, ...]
-        bounds = [0]
-        if B > cb and cb >= 64:
-            bounds += [cb // 4, cb]
-        while bounds[-1] < B:
-            bounds.append(min(bounds[-1] + cb, B))
         feats = torch.empty(cb * T * F, dtype=torch.float32, device=dev)
         scratch = torch.empty(max(int(L.lib().vp_frontend_scratch_floats(eng.handle, cb, lmax)), 1), dtype=torch.float32,
                               device=dev)
-        dwave = [torch.empty(cb * lmax, dtype=torch.float32, device=dev) for _ in range(2)]
+        dwave = [torch.empty(cb * lmax, dtype=torch.float32, device=dev) for _ in range(2 if B > cb else 1)]
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
         free_ev = [None, None]                       # compute finished reading device/pinned slot
-        for ci in range(len(bounds) - 1):
-            lo, hi = bounds[ci], bounds[ci + 1]
+        for ci, lo in enumerate(range(0, B, cb)):
+            hi = min(lo + cb, B)
             n = hi - lo
             slot = ci & 1
             if free_ev[slot] is not None:
-                free_ev[slot].synchronize()          # pinned slot may be overwritten only after its H2D + kernels
+                free_ev[slot].synchronize()          # pinned + device slot reusable once its kernels finished
             host = self._pinned_slot(slot, n * lmax).view(n, lmax)
-            # zero padding to the global longest item (predict.py:248-254): native multi-threaded gather (GIL released)
-            ptrs = (C.c_void_p * n)(*[w.ctypes.data for w in waves[lo:hi]])
-            lens = (C.c_int32 * n)(*[w.shape[0] for w in waves[lo:hi]])
-            rc = L.lib().vp_host_gather_pad(ptrs, lens, n, lmax, C.c_void_p(host.data_ptr()), self.GATHER_THREADS)
-            if rc != 0:
-                raise RuntimeError(f'vp_host_gather_pad failed ({rc})')
             dw = dwave[slot][:n * lmax].view(n, lmax)
-            with torch.cuda.stream(self._copy_stream):
-                dw.copy_(host, non_blocking=True)
-                copied = torch.cuda.Event()
-                copied.record(self._copy_stream)
+            for s0 in range(0, n, self.COPY_SLICE):  # gather slice -> enqueue its H2D -> gather next slice ...
+                s1 = min(s0 + self.COPY_SLICE, n)
+                m = s1 - s0
+                ptrs = (C.c_void_p * m)(*[w.ctypes.data for w in waves[lo + s0:lo + s1]])
+                lens = (C.c_int32 * m)(*[w.shape[0] for w in waves[lo + s0:lo + s1]])
+                rc = L.lib().vp_host_gather_pad(ptrs, lens, m, lmax, C.c_void_p(host[s0:s1].data_ptr()),
+                                                self.GATHER_THREADS)
+                if rc != 0:
+                    raise RuntimeError(f'vp_host_gather_pad failed ({rc})')
+                with torch.cuda.stream(self._copy_stream):
+                    dw[s0:s1].copy_(host[s0:s1], non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(self._copy_stream)
             main.wait_event(copied)
             keep = keep_all[lo:hi] if keep_all is not None else None
             self.predictor.program(n, T).run_wave(dw, keep, feats, scratch, emb[lo:hi])
             done = torch.cuda.Event()
             done.record(main)
-            free_ev[slot] = done                     # slot (pinned + device) reusable once these kernels finished
+            free_ev[slot] = done
         return emb.cpu().numpy()
 
     def predict(self, audio_data, sample_rate=16000):
