@@ -11,7 +11,6 @@ Differences that are deliberate:
   * ``speaker_diarization`` (predict.py:365-395: VAD + spectral clustering on CPU) is outside the hot path and raises
     NotImplementedError.
 """
-import ctypes as C
 import os
 import pickle
 import shutil
@@ -59,6 +58,7 @@ class MVectorPredictor:
         self.predictor.eval()
         self._pinned = None
         self._copy_stream = None
+        self._pool = None
 
         self.audio_feature = None
         self.audio_feature_mean = None
@@ -173,10 +173,9 @@ class MVectorPredictor:
             audio_segment.normalize(target_db=ds.target_dB)
         return audio_segment
 
-    #: utterances per compute chunk (one fused vp_embed_wave call each) and per host-gather / H2D slice
-    CHUNK = int(os.environ.get('VPB_PREDICT_CHUNK', '256'))
-    COPY_SLICE = int(os.environ.get('VPB_COPY_SLICE', '64'))
-    GATHER_THREADS = int(os.environ.get('VPB_GATHER_THREADS', '8'))
+    #: utterances per pipeline chunk of predict_batch (host gather + H2D of chunk k+1 overlap the kernels of chunk k)
+    CHUNK = int(os.environ.get('VPB_PREDICT_CHUNK', '128'))
+    GATHER_THREADS = 4
 
     def _pinned_slot(self, slot, n):
         """Two reusable pinned host staging buffers (double buffering)."""
@@ -190,11 +189,12 @@ class MVectorPredictor:
         """waves: list of 1-D float32 arrays (already loaded / resampled / normalised) -> np.float32 [B, embd_dim].
 
         Reference semantics (predict.py:244-262): every utterance is zero padded to the longest item of the WHOLE list,
-        T and the CMN mean follow that padded length, frames >= round(len/Lmax * T) are zeroed.  Host side: the list is
-        gathered into pinned memory in slices of COPY_SLICE utterances by a native multi-threaded copy and each slice's
-        H2D transfer is enqueued on a copy stream while the next slice is gathered; the kernels then run over compute
-        chunks of CHUNK utterances (measured on B200: splitting 256 utterances into smaller compute chunks costs more
-        GPU efficiency than the overlap buys).  One D2H of the [B, embd] result at the end."""
+        T and the CMN mean follow that padded length, frames >= round(len/Lmax * T) are zeroed.  Because every op is
+        per-utterance, the list is processed in chunks of CHUNK utterances: while the GPU runs the fused
+        ``vp_embed_wave`` of chunk k, the host gathers chunk k+1 into pinned memory (a few threads; numpy releases the GIL
+        while copying) and its H2D copy runs on a second stream.  One D2H of the [B, embd] result at the end.  Measured on
+        B200 at B=256: two chunks of 128 are the best trade-off (smaller compute chunks lose more GPU efficiency than the
+        overlap buys; a single chunk exposes the whole 49 MB host gather)."""
         from . import _lib as L
         B = len(waves)
         fz = self._audio_featurizer
@@ -213,7 +213,7 @@ class MVectorPredictor:
         feats = torch.empty(cb * T * F, dtype=torch.float32, device=dev)
         scratch = torch.empty(max(int(L.lib().vp_frontend_scratch_floats(eng.handle, cb, lmax)), 1), dtype=torch.float32,
                               device=dev)
-        dwave = [torch.empty(cb * lmax, dtype=torch.float32, device=dev) for _ in range(2 if B > cb else 1)]
+        dwave = [torch.empty(cb * lmax, dtype=torch.float32, device=dev) for _ in range(2)]
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
@@ -223,28 +223,35 @@ class MVectorPredictor:
             n = hi - lo
             slot = ci & 1
             if free_ev[slot] is not None:
-                free_ev[slot].synchronize()          # pinned + device slot reusable once its kernels finished
+                free_ev[slot].synchronize()          # pinned slot may be overwritten only after its H2D + kernels
             host = self._pinned_slot(slot, n * lmax).view(n, lmax)
+            hnp = host.numpy()
+            def fill(r0, r1, hnp=hnp, lo=lo):          # zero padding to the global longest item (predict.py:248-254)
+                for i in range(r0, r1):
+                    w = waves[lo + i]
+                    m = w.shape[0]
+                    hnp[i, :m] = w
+                    if m < lmax:
+                        hnp[i, m:] = 0.0
+            if n >= 32 and self.GATHER_THREADS > 1:   # numpy releases the GIL while copying: gather with a few threads
+                if self._pool is None:
+                    from concurrent.futures import ThreadPoolExecutor
+                    self._pool = ThreadPoolExecutor(max_workers=self.GATHER_THREADS)
+                step = -(-n // self.GATHER_THREADS)
+                list(self._pool.map(lambda r: fill(r, min(r + step, n)), range(0, n, step)))
+            else:
+                fill(0, n)
             dw = dwave[slot][:n * lmax].view(n, lmax)
-            for s0 in range(0, n, self.COPY_SLICE):  # gather slice -> enqueue its H2D -> gather next slice ...
-                s1 = min(s0 + self.COPY_SLICE, n)
-                m = s1 - s0
-                ptrs = (C.c_void_p * m)(*[w.ctypes.data for w in waves[lo + s0:lo + s1]])
-                lens = (C.c_int32 * m)(*[w.shape[0] for w in waves[lo + s0:lo + s1]])
-                rc = L.lib().vp_host_gather_pad(ptrs, lens, m, lmax, C.c_void_p(host[s0:s1].data_ptr()),
-                                                self.GATHER_THREADS)
-                if rc != 0:
-                    raise RuntimeError(f'vp_host_gather_pad failed ({rc})')
-                with torch.cuda.stream(self._copy_stream):
-                    dw[s0:s1].copy_(host[s0:s1], non_blocking=True)
-            copied = torch.cuda.Event()
-            copied.record(self._copy_stream)
+            with torch.cuda.stream(self._copy_stream):
+                dw.copy_(host, non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(self._copy_stream)
             main.wait_event(copied)
             keep = keep_all[lo:hi] if keep_all is not None else None
             self.predictor.program(n, T).run_wave(dw, keep, feats, scratch, emb[lo:hi])
             done = torch.cuda.Event()
             done.record(main)
-            free_ev[slot] = done
+            free_ev[slot] = done                     # slot (pinned + device) reusable once these kernels finished
         return emb.cpu().numpy()
 
     def predict(self, audio_data, sample_rate=16000):
