@@ -316,3 +316,55 @@ def test_c5_eres2net55m_ragged_1_to_10s():
     fz = _featurizer(dict(feature_method='Fbank', method_args=fargs))
     got = _model('ERes2Net', 80, margs, sd)(fz(torch.from_numpy(x), torch.from_numpy(ratio))).cpu().numpy()
     assert rel_l2(got, ref).max() < EMB_TOL
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize('n_fft,hop,n_mels', [(256, 128, 32), (2048, 512, 80)])
+def test_melspectrogram_fft_sizes(n_fft, hop, n_mels):
+    """All power-of-two FFT sizes of the Stockham kernel (256 = 4^4, 2048 = 4^5 * 2: radix-2 tail pass)."""
+    import warnings
+    from oracle import frontend as ofe
+    margs = dict(sample_rate=16000, n_fft=n_fft, hop_length=hop, n_mels=n_mels)
+    g = torch.Generator().manual_seed(n_fft)
+    w = torch.randn(2, 20000, generator=g) * 0.1
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref = ofe.featurize(w, None, 'MelSpectrogram', margs)
+        fz = _featurizer(dict(feature_method='MelSpectrogram', method_args=margs))
+    got = fz(w).cpu()
+    assert got.shape == ref.shape
+    assert ((got - ref).abs().max() / ref.abs().max()).item() < 2e-6
+
+
+def test_short_and_long_utterances(manifest):
+    """Shortest accepted audio (min_duration 0.3 s -> 28 frames) and a 14 s utterance (T = 1398 > 800: the attentive
+    pooling kernel leaves its shared-memory path; CAM++ gets 7 context segments)."""
+    from oracle import frontend as ofe
+    from oracle import models as om
+    for name in ('ecapa_small', 'campplus_small'):
+        m = manifest[name]
+        _, sd = load_golden(name)
+        model = _model(m['model'], m['feature_dim'], m['model_args'], sd)
+        fz = _featurizer(m['preprocess'])
+        for lens, seed in (([4800], 1), ([224000, 100000], 2)):
+            waves = _ragged(lens, seed)
+            x, ratio = ofe.pad_batch(waves)
+            fa, fm = m['preprocess']['feature_method'], m['preprocess']['method_args']
+            rr = None if len(lens) == 1 else ratio
+            ref = om.forward(m['model'], sd, ofe.featurize(x, rr, fa, fm), **m['model_args']).numpy()
+            got = model(fz(torch.from_numpy(x), None if rr is None else torch.from_numpy(rr))).cpu().numpy()
+            assert rel_l2(got, ref).max() < EMB_TOL, (name, lens)
+
+
+def test_batch_of_one_and_odd_batches():
+    """M tails: B*T not a multiple of the 128-row MMA tile, B = 1 (tiny-M engine selection)."""
+    from oracle import models as om
+    margs = dict(embd_dim=192, pooling_type='ASP', channels=[512, 512, 512, 512, 1536])
+    sd = om.random_state_dict('EcapaTdnn', 80, seed=11, **margs)
+    model = _model('EcapaTdnn', 80, margs, sd)
+    g = torch.Generator().manual_seed(4)
+    for B, T in ((1, 61), (5, 333), (7, 101)):
+        feats = torch.randn(B, T, 80, generator=g) * 2.0
+        ref = om.forward('EcapaTdnn', sd, feats, **margs).numpy()
+        got = model(feats.cuda()).cpu().numpy()
+        assert rel_l2(got, ref).max() < EMB_TOL, (B, T)
