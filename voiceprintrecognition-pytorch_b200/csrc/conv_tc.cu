@@ -566,8 +566,12 @@ cudaError_t launch_conv_tc(const ConvParams& p, cudaStream_t stream) {
   a.k_blocks = (p.K + BK - 1) / BK;
   a.kc = tc_chunked(p.K) ? KC_BLOCKS : a.k_blocks;
   a.n_chunks = (a.k_blocks + a.kc - 1) / a.kc;
+  // accumulator regions [acc*BN, +BN) (+ running sum at 2*BN when chunked); tcgen05.ld reads 32 columns at a time, so
+  // the last 32-column read of the last region must stay inside the allocation
+  const int regions = a.n_chunks > 1 ? 3 : 2;
+  const int need = (regions - 1) * a.BN + ((a.BN + 31) / 32) * 32;
   int cols = 32;
-  while (cols < (a.n_chunks > 1 ? 3 : 2) * a.BN) cols <<= 1;
+  while (cols < need || cols < regions * a.BN) cols <<= 1;
   if (cols > 512) return cudaErrorInvalidConfiguration;
   a.tmem_cols = cols;
   static int debug_flags = -1;
