@@ -368,3 +368,43 @@ def test_batch_of_one_and_odd_batches():
         ref = om.forward('EcapaTdnn', sd, feats, **margs).numpy()
         got = model(feats.cuda()).cpu().numpy()
         assert rel_l2(got, ref).max() < EMB_TOL, (B, T)
+
+
+def test_extract_features_npy_cache(tmp_path):
+    """MVectorTrainer.extract_features (trainer.py:146-175) writes the [T, F] float32 .npy cache
+    + ``*_features.txt`` lists that the reference's reader consumes (reader.py:76-81)."""
+    from mvector.trainer import MVectorTrainer
+    from oracle import frontend as ofe
+    g = torch.Generator().manual_seed(9)
+    lists = {}
+    for nm, lens in (('train', [16000, 2000, 24000]), ('enroll', [12000]), ('trials', [9000])):
+        lines = []
+        for i, n in enumerate(lens):
+            p = tmp_path / f'{nm}_{i}.wav'
+            pcm = (torch.randn(n, generator=g) * 3000).to(torch.int16).numpy()
+            with wave.open(str(p), 'wb') as w:
+                w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000); w.writeframes(pcm.astype('<i2').tobytes())
+            lines.append(f'{p}\t{i}')
+        lp = tmp_path / f'{nm}_list.txt'
+        lp.write_text('\n'.join(lines) + '\n')
+        lists[nm] = str(lp)
+    fargs = dict(sample_frequency=16000, num_mel_bins=80)
+    cfg = {'dataset_conf': {'dataset': {'min_duration': 0.3, 'sample_rate': 16000, 'use_dB_normalization': True,
+                                        'target_dB': -20},
+                            'train_list': lists['train'], 'enroll_list': lists['enroll'], 'trials_list': lists['trials']},
+           'preprocess_conf': {'feature_method': 'Fbank', 'method_args': fargs}}
+    MVectorTrainer(cfg, use_gpu=True).extract_features(save_dir=str(tmp_path / 'features'), max_duration=1.2)
+    out = (tmp_path / 'train_list_features.txt').read_text().splitlines()
+    assert len(out) == 3                                 # the 0.125 s file is replaced by its successor (reader.py:86-88)
+    for ln in out + (tmp_path / 'enroll_list_features.txt').read_text().splitlines():
+        path, label = ln.split('\t')
+        f = np.load(path)
+        assert f.dtype == np.float32 and f.ndim == 2 and f.shape[1] == 80
+        assert f.shape[0] <= 1 + (int(1.2 * 16000) - 400) // 160          # cropped to max_duration
+    # content check of the first file against the oracle
+    from mvector.audio import AudioSegment
+    seg = AudioSegment.from_file(str(tmp_path / 'train_0.wav'))
+    seg.normalize(-20)
+    ref = ofe.featurize(seg.samples, None, 'Fbank', fargs)[0].numpy()
+    got = np.load(out[0].split('\t')[0])
+    assert got.shape == ref.shape and np.abs(got - ref).max() < FBANK_ABS_TOL
