@@ -48,24 +48,21 @@ class MVectorTrainer(object):
                 lines = [ln for ln in f.read().splitlines() if ln.strip()]
             save_data_list = data_list.replace('.txt', '_features.txt')
             with open(save_data_list, 'w', encoding='utf-8') as out:
-                i = 0
-                done = 0
-                while done < len(lines):
-                    # reader.py:86-88,102-106: a short / unreadable file is replaced by the next one of the list
-                    path, label = lines[i].split('\t')
-                    done += 1
+                for idx in range(len(lines)):
+                    # reader.py:86-88,102-106: a short / unreadable file is replaced by its successor in the list
+                    j, seg = idx, None
                     for _ in range(len(lines)):
+                        path, label = lines[j].split('\t')
                         try:
-                            seg = AudioSegment.from_file(path)
-                            if seg.duration >= min_duration:
+                            cand = AudioSegment.from_file(path)
+                            if cand.duration >= min_duration:
+                                seg = cand
                                 break
                         except Exception as e:  # noqa: BLE001  (the reference logs and moves on, reader.py:103-106)
                             logger.error(f"[{path}]特征提取失败，错误信息：{e}")
-                        i = i + 1 if i < len(lines) - 1 else 0
-                        path, label = lines[i].split('\t')
-                    else:
+                        j = j + 1 if j < len(lines) - 1 else 0
+                    if seg is None:
                         raise RuntimeError('no usable audio file in ' + data_list)
-                    i = i + 1 if i < len(lines) - 1 else 0
                     if seg.sample_rate != sample_rate:
                         seg.resample(sample_rate)
                     if use_db:
