@@ -176,6 +176,7 @@ class MVectorPredictor:
     #: utterances per pipeline chunk of predict_batch (host gather + H2D of chunk k+1 overlap the kernels of chunk k)
     CHUNK = int(os.environ.get('VPB_PREDICT_CHUNK', '128'))
     GATHER_THREADS = 4
+    COPY_SLICE = int(os.environ.get('VPB_COPY_SLICE', '32'))
 
     def _pinned_slot(self, slot, n):
         """Two reusable pinned host staging buffers (double buffering)."""
@@ -233,19 +234,24 @@ class MVectorPredictor:
                     hnp[i, :m] = w
                     if m < lmax:
                         hnp[i, m:] = 0.0
-            if n >= 32 and self.GATHER_THREADS > 1:   # numpy releases the GIL while copying: gather with a few threads
-                if self._pool is None:
-                    from concurrent.futures import ThreadPoolExecutor
-                    self._pool = ThreadPoolExecutor(max_workers=self.GATHER_THREADS)
-                step = -(-n // self.GATHER_THREADS)
-                list(self._pool.map(lambda r: fill(r, min(r + step, n)), range(0, n, step)))
-            else:
-                fill(0, n)
             dw = dwave[slot][:n * lmax].view(n, lmax)
-            with torch.cuda.stream(self._copy_stream):
-                dw.copy_(host, non_blocking=True)
-                copied = torch.cuda.Event()
-                copied.record(self._copy_stream)
+            # gather in slices (a few threads; numpy releases the GIL while copying) and enqueue each slice's H2D as soon as
+            # it is staged, so the transfer of slice k overlaps the gather of slice k+1
+            sl = max(8, self.COPY_SLICE)
+            for s0 in range(0, n, sl):
+                s1 = min(s0 + sl, n)
+                if s1 - s0 >= 16 and self.GATHER_THREADS > 1:
+                    if self._pool is None:
+                        from concurrent.futures import ThreadPoolExecutor
+                        self._pool = ThreadPoolExecutor(max_workers=self.GATHER_THREADS)
+                    step = -(-(s1 - s0) // self.GATHER_THREADS)
+                    list(self._pool.map(lambda r: fill(r, min(r + step, s1)), range(s0, s1, step)))
+                else:
+                    fill(s0, s1)
+                with torch.cuda.stream(self._copy_stream):
+                    dw[s0:s1].copy_(host[s0:s1], non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(self._copy_stream)
             main.wait_event(copied)
             keep = keep_all[lo:hi] if keep_all is not None else None
             self.predictor.program(n, T).run_wave(dw, keep, feats, scratch, emb[lo:hi])
