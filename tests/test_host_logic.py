@@ -155,3 +155,23 @@ def test_default_model_plans_lower_and_fit(manifest):
         pb = m.lower(B, T)
         assert pb.in_floats == B * T * fdim and pb.out_floats == B * 192
         assert pb.peak < 40 * 2 ** 30
+
+
+def test_host_gather_pad_native():
+    """vp_host_gather_pad: the zero-padded [n, lmax] staging matrix of predict.py:248-254, multi-threaded, no GPU."""
+    import ctypes as C
+    from mvector import _lib as L
+    rng = np.random.default_rng(3)
+    lens = [int(x) for x in rng.integers(1, 5000, size=37)] + [5000]
+    ws = [rng.standard_normal(n).astype(np.float32) for n in lens]
+    lmax = max(lens)
+    dst = np.full((len(ws), lmax), np.nan, dtype=np.float32)
+    ptrs = (C.c_void_p * len(ws))(*[w.ctypes.data for w in ws])
+    ln = (C.c_int32 * len(ws))(*lens)
+    for threads in (1, 4):
+        dst[:] = np.nan
+        assert L.lib().vp_host_gather_pad(ptrs, ln, len(ws), lmax, dst.ctypes.data_as(C.c_void_p), threads) == 0
+        for i, w in enumerate(ws):
+            assert np.array_equal(dst[i, :len(w)], w) and not dst[i, len(w):].any()
+    bad = (C.c_int32 * len(ws))(*([lmax + 1] + lens[1:]))
+    assert L.lib().vp_host_gather_pad(ptrs, bad, len(ws), lmax, dst.ctypes.data_as(C.c_void_p), 2) == L.VP_ERR_INVALID

@@ -140,9 +140,6 @@ class View:
         return View(self.off, self.ld, self.coff + start, n)
 
 
-INPUT = 'input'
-OUTPUT = 'output'
-
 
 class PlanBuilder:
     """Accumulates vp_ops and plans the workspace (first-fit free list: buffers are freed explicitly by the model
@@ -376,13 +373,3 @@ class Program:
         if self._p:
             L.lib().vp_program_destroy(self._p)
             self._p = C.c_void_p()
-
-
-_ENGINES = {}
-
-
-def get_engine(device=None):
-    idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
-    if idx not in _ENGINES:
-        _ENGINES[idx] = Engine(idx)
-    return _ENGINES[idx]
