@@ -91,10 +91,12 @@ int vp_melspec(vp_handle* h, const float* wave, int32_t B, int32_t Lpad, const i
  * ---------------------------------------------------------------------------------------------------------- */
 enum {                       /* vp_op.kind */
   VP_OP_CONV = 1,            /* implicit-GEMM conv1d/conv2d/linear with fused prologue + epilogue */
-  VP_OP_CONV_C1 = 2,         /* 3x3 conv2d with Cin = 1 on the feature map [B,T,F] -> [B,T,F,C] */
+  VP_OP_CONV_C1 = 2,         /* KTxKF (<= 7x7) strided conv2d with Cin = 1 on the feature map [B,T,F] -> [B,T',F',C] */
   VP_OP_COLSTATS = 3,        /* per-utterance column statistics over rows (mean / mean+std variants / segments) */
   VP_OP_ASP_POOL = 4,        /* softmax over T of logits, attentive mean + std (pooling.py:122-126); mode 1 = mean only (SAP, pooling.py:62-64) */
-  VP_OP_EW = 5               /* elementwise: gate*x + residual, AFF blend, copy */
+  VP_OP_EW = 5,              /* elementwise: gate*x + residual, AFF blend, copy */
+  VP_OP_POOL2D = 6           /* KTxKF max / average pooling on a channel-last 2-D map (res2net.py:33-34,105); mode 0 = max
+                                (implicit -inf padding), 1 = average with count_include_pad (zero padding, divide by KT*KF) */
 };
 enum { VP_ACT_NONE = 0, VP_ACT_RELU = 1, VP_ACT_HARDTANH20 = 2, VP_ACT_SIGMOID = 3, VP_ACT_TANH = 4, VP_ACT_SILU = 5 };
 enum { VP_PAD_ZERO = 0, VP_PAD_REFLECT = 1 };

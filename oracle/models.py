@@ -466,6 +466,74 @@ def eres2net_forward(sd, x, num_blocks=(3, 4, 6, 3), m_channels=32, mul_channel=
 
 
 # ---------------------------------------------------------------------------------------------
+# Res2Net (res2net.py:89-174)
+# ---------------------------------------------------------------------------------------------
+def _res2net_blocks(m_channels, layers, base_width):
+    inpl = m_channels
+    for li, nb in enumerate(layers, start=1):
+        planes = m_channels * (2 ** (li - 1))
+        stride = 1 if li == 1 else 2
+        for b in range(nb):
+            first = b == 0
+            ds = first and (stride != 1 or inpl != planes * 4)
+            yield f'layer{li}.{b}', inpl, planes, int(math.floor(planes * (base_width / 64.0))), (stride if first else 1), \
+                ('stage' if first else 'normal'), ds
+            inpl = planes * 4
+
+
+def res2net_param_shapes(input_size, m_channels=32, layers=(3, 4, 6, 3), base_width=32, scale=2, embd_dim=192,
+                         pooling_type='ASP'):
+    d = OrderedDict()
+    d['conv1.weight'] = (m_channels, 1, 7, 7)
+    _bn_shapes(d, 'bn1', m_channels)
+    nums = 1 if scale == 1 else scale - 1
+    for p, inpl, planes, width, stride, stype, ds in _res2net_blocks(m_channels, layers, base_width):
+        d[p + '.conv1.weight'] = (width * scale, inpl, 1, 1)
+        _bn_shapes(d, p + '.bn1', width * scale)
+        for j in range(nums):
+            d[f'{p}.convs.{j}.weight'] = (width, width, 3, 3)
+        for j in range(nums):
+            _bn_shapes(d, f'{p}.bns.{j}', width)
+        d[p + '.conv3.weight'] = (planes * 4, width * scale, 1, 1)
+        _bn_shapes(d, p + '.bn3', planes * 4)
+        if ds:
+            d[p + '.downsample.0.weight'] = (planes * 4, inpl, 1, 1)
+            _bn_shapes(d, p + '.downsample.1', planes * 4)
+    cat = m_channels * 8 * 4 * (input_size // base_width)
+    width = _pool_shapes(d, 'pooling', pooling_type, cat, 128)
+    _bn_shapes(d, 'bn2', width)
+    d['linear.weight'] = (embd_dim, width)
+    d['linear.bias'] = (embd_dim,)
+    _bn_shapes(d, 'bn3', embd_dim)
+    return d
+
+
+def res2net_forward(sd, x, m_channels=32, layers=(3, 4, 6, 3), base_width=32, scale=2, embd_dim=192, pooling_type='ASP'):
+    x = x.transpose(2, 1).unsqueeze(1)
+    x = F.relu(_bn(sd, 'bn1', F.conv2d(x, sd['conv1.weight'], stride=3, padding=1)))        # res2net.py:100,144-146
+    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    nums = 1 if scale == 1 else scale - 1
+    for p, inpl, planes, width, stride, stype, ds in _res2net_blocks(m_channels, layers, base_width):
+        out = F.relu(_bn(sd, p + '.bn1', F.conv2d(x, sd[p + '.conv1.weight'])))
+        spx = torch.split(out, width, 1)
+        pieces = []
+        for j in range(nums):                                                                  # res2net.py:58-69
+            sp = spx[j] if (j == 0 or stype == 'stage') else sp + spx[j]
+            sp = F.relu(_bn(sd, f'{p}.bns.{j}', F.conv2d(sp, sd[f'{p}.convs.{j}.weight'], stride=stride, padding=1)))
+            pieces.append(sp)
+        if scale != 1:
+            pieces.append(spx[nums] if stype == 'normal' else F.avg_pool2d(spx[nums], kernel_size=3, stride=stride, padding=1))
+        out = _bn(sd, p + '.bn3', F.conv2d(torch.cat(pieces, 1), sd[p + '.conv3.weight']))
+        res = x
+        if ds:
+            res = _bn(sd, p + '.downsample.1', F.conv2d(x, sd[p + '.downsample.0.weight'], stride=stride))
+        x = F.relu(out + res)
+    x = x.reshape(x.shape[0], -1, x.shape[-1])
+    x = _bn(sd, 'bn2', pool_forward(sd, 'pooling', pooling_type, x))
+    return _bn(sd, 'bn3', F.linear(x, sd['linear.weight'], sd['linear.bias']))
+
+
+# ---------------------------------------------------------------------------------------------
 # registry (mvector/models/__init__.py:15-21 builds by class name with **model_args)
 # ---------------------------------------------------------------------------------------------
 MODELS = {
@@ -474,6 +542,7 @@ MODELS = {
     'CAMPPlus': (campplus_param_shapes, campplus_forward),
     'ResNetSE': (resnetse_param_shapes, resnetse_forward),
     'ERes2Net': (eres2net_param_shapes, eres2net_forward),
+    'Res2Net': (res2net_param_shapes, res2net_forward),
 }
 
 
@@ -492,7 +561,7 @@ def forward(model, sd, feats, **model_args):
 #: itself differs from fp64 by 1e-4 (6.6M) / 4e-3 (55M) -- even changing the CPU thread count moves it by 2e-3), so a
 #: 1e-4 parity gate would measure noise.  These gains bring the input->embedding amplification to O(1) (like a trained
 #: net) and the fp32-vs-fp64 floor to <= 2e-6 while keeping every layer's contribution visible (measured in round 1).
-CONDITIONED_GAIN = {'EcapaTdnn': 1.0, 'TDNN': 1.0, 'CAMPPlus': 1.0, 'ResNetSE': 0.8, 'ERes2Net': 0.7}
+CONDITIONED_GAIN = {'EcapaTdnn': 1.0, 'TDNN': 1.0, 'CAMPPlus': 1.0, 'ResNetSE': 0.8, 'ERes2Net': 0.7, 'Res2Net': 0.8}
 
 
 def random_state_dict(model, input_size, seed=0, gain=1.0, **model_args):

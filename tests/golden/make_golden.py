@@ -98,6 +98,8 @@ CASES = {
     'tdnn_tsp_small': ('TDNN', dict(embd_dim=32, channels=64, pooling_type='TSP'), FBANK24, [9600, 8000]),
     'resnetse_tap_small': ('ResNetSE', dict(embd_dim=32, layers=[1, 1, 1, 1], num_filters=[16, 16, 32, 32],
                                             pooling_type='TAP'), MEL16, [12000, 11000]),
+    'res2net_small': ('Res2Net', dict(embd_dim=32, m_channels=8, layers=[1, 2, 1, 1], base_width=32, scale=2,
+                                      pooling_type='ASP'), MEL64, [16000, 12000]),
     'eres2net_wide_small': ('ERes2Net', dict(embd_dim=32, num_blocks=[1, 1, 1, 1], m_channels=8, mul_channel=2,
                                              expansion=4, base_width=32, scale=3), FBANK24, [12000]),
 }
@@ -193,6 +195,7 @@ def main():
         'ResNetSE': (64, dict(embd_dim=192, pooling_type='ASP')),
         'ERes2Net': (80, dict(embd_dim=192, m_channels=32)),
         'ERes2Net55M': (80, dict(embd_dim=192, m_channels=64, mul_channel=2, expansion=4, base_width=24, scale=3)),
+        'Res2Net': (80, dict(embd_dim=192, pooling_type='ASP', m_channels=32)),
     }
     digests = {}
     for key, (fdim, margs) in defaults.items():

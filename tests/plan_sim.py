@@ -61,7 +61,7 @@ class Sim:
     def run(self):
         for o in self.pb.ops:
             {L.OP_CONV: self.conv, L.OP_CONV_C1: self.conv, L.OP_COLSTATS: self.colstats,
-             L.OP_ASP_POOL: self.asp, L.OP_EW: self.ew}[o.kind](o)
+             L.OP_ASP_POOL: self.asp, L.OP_EW: self.ew, L.OP_POOL2D: self.pool2d}[o.kind](o)
         assert not np.isnan(self.out).any(), 'program output not fully written'
         return self.out.copy()
 
@@ -152,6 +152,16 @@ class Sim:
             return
         sd = np.sqrt(np.maximum((a * (X - mean[:, None]) ** 2).sum(1), o.eps))
         self.wr(o.dst, o.B, o.out_ld, o.out_coff, 2 * Cn, np.concatenate([mean, sd], 1))
+
+    def pool2d(self, o):
+        X = self.rd(o.src, o.B * o.Tin * o.Fin, o.in_ld, o.in_coff, o.Cin).reshape(o.B, o.Tin, o.Fin, o.Cin)
+        out = np.zeros((o.B, o.Tout, o.Fout, o.Cin))
+        for to in range(o.Tout):
+            for fo in range(o.Fout):
+                t0, f0 = to * o.sT - o.padT, fo * o.sF - o.padF
+                win = X[:, max(t0, 0):min(t0 + o.KT, o.Tin), max(f0, 0):min(f0 + o.KF, o.Fin)]
+                out[:, to, fo] = win.max(axis=(1, 2)) if o.mode == 0 else win.sum(axis=(1, 2)) / (o.KT * o.KF)
+        self.wr(o.dst, o.B * o.Tout * o.Fout, o.out_ld, o.out_coff, o.Cin, out.reshape(-1, o.Cin))
 
     def ew(self, o):
         rpu = o.Tin * o.Fin

@@ -250,10 +250,10 @@ static int validate_op(vp_program* p, const vp_op& o, int i) {
       const long long rows_in = (long long)o.B * o.Tin * o.Fin, rows_out = (long long)o.B * o.Tout * o.Fout;
       if (rows_out > 0x7fffffffLL || rows_in > 0x7fffffffLL) return fail(h, VP_ERR_UNSUPPORTED, "op %d: > 2^31 rows", i);
       if (o.kind == VP_OP_CONV_C1) {
-        if (o.Cin != 1 || o.KT != 3 || o.KF != 3 || o.sT != 1 || o.sF != 1 || o.dT != 1 || o.dF != 1 || (o.Cout & 3) ||
+        if (o.Cin != 1 || o.KT > 7 || o.KF > 7 || (o.Cout & 3) || o.w_ld < o.KT * o.KF ||
             o.src2_mode != VP_SRC2_NONE || o.pre_s >= 0 || (o.out_ld & 3) || (o.out_coff & 3) || o.pad_mode != VP_PAD_ZERO)
-          return fail(h, VP_ERR_UNSUPPORTED, "op %d: CONV_C1 is 3x3/s1/zero-pad with Cin=1, Cout%%4==0", i);
-        TRY(check_w(p, "w", o.w, view_floats(o.Cout, o.w_ld, 0, 9), i));
+          return fail(h, VP_ERR_UNSUPPORTED, "op %d: CONV_C1 is a <=7x7 zero-padded conv with Cin=1, Cout%%4==0", i);
+        TRY(check_w(p, "w", o.w, view_floats(o.Cout, o.w_ld, 0, o.KT * o.KF), i));
       } else {
         if ((o.Cin & 3) || (cin_tot & 3) || (o.in_ld & 3) || (o.in_coff & 3) || (o.w_ld & 3))
           return fail(h, VP_ERR_UNSUPPORTED, "op %d: CONV needs Cin/in_ld/in_coff/w_ld multiples of 4", i);
@@ -305,6 +305,18 @@ static int validate_op(vp_program* p, const vp_op& o, int i) {
       TRY(check_act_buf(p, "logits", o.src2, view_floats(rows, o.src2_ld, o.src2_coff, o.Cin), false, i));
       if (o.mode != 0 && o.mode != 1) return fail(h, VP_ERR_INVALID, "op %d: asp mode", i);
       TRY(check_act_buf(p, "dst", o.dst, view_floats(o.B, o.out_ld, o.out_coff, (o.mode == 1 ? 1 : 2) * o.Cin), true, i));
+      return VP_OK;
+    }
+    case VP_OP_POOL2D: {
+      if (o.Tin < 1 || o.Fin < 1 || o.Tout < 1 || o.Fout < 1 || o.KT < 1 || o.KF < 1 || o.sT < 1 || o.sF < 1 || o.padT < 0 ||
+          o.padF < 0 || o.Cin < 4 || (o.Cin & 3) || (o.in_ld & 3) || (o.in_coff & 3) || (o.out_ld & 3) || (o.out_coff & 3) ||
+          (o.mode != 0 && o.mode != 1))
+        return fail(h, VP_ERR_INVALID, "op %d: pool geometry / alignment", i);
+      if ((long long)(o.Tout - 1) * o.sT - o.padT >= o.Tin || (long long)(o.Fout - 1) * o.sF - o.padF >= o.Fin ||
+          o.padT >= o.KT || o.padF >= o.KF)
+        return fail(h, VP_ERR_INVALID, "op %d: pooling window entirely outside the map", i);
+      TRY(check_act_buf(p, "src", o.src, view_floats((long long)o.B * o.Tin * o.Fin, o.in_ld, o.in_coff, o.Cin), false, i));
+      TRY(check_act_buf(p, "dst", o.dst, view_floats((long long)o.B * o.Tout * o.Fout, o.out_ld, o.out_coff, o.Cin), true, i));
       return VP_OK;
     }
     case VP_OP_EW: {
@@ -445,6 +457,15 @@ static int run_ops(vp_program* p, const float* feats, float* emb, cudaStream_t s
         a.B = o.B; a.T = o.Tin; a.C = o.Cin; a.x_ld = o.in_ld; a.x_coff = o.in_coff; a.l_ld = o.src2_ld;
         a.l_coff = o.src2_coff; a.out_ld = o.out_ld; a.out_coff = o.out_coff; a.eps = o.eps; a.mean_only = o.mode == 1;
         CUDA_TRY(h, launch_asp_pool(a, st));
+        break;
+      }
+      case VP_OP_POOL2D: {
+        PoolParams q;
+        q.src = rd(p, o.src, feats, emb); q.dst = const_cast<float*>(rd(p, o.dst, feats, emb));
+        q.B = o.B; q.Tin = o.Tin; q.Fin = o.Fin; q.Tout = o.Tout; q.Fout = o.Fout; q.C = o.Cin;
+        q.in_ld = o.in_ld; q.in_coff = o.in_coff; q.out_ld = o.out_ld; q.out_coff = o.out_coff;
+        q.KT = o.KT; q.KF = o.KF; q.sT = o.sT; q.sF = o.sF; q.padT = o.padT; q.padF = o.padF; q.mode = o.mode;
+        CUDA_TRY(h, launch_pool2d(q, st));
         break;
       }
       case VP_OP_EW: {

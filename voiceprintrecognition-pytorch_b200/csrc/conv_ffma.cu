@@ -217,39 +217,43 @@ cudaError_t launch_conv_ffma(const ConvParams& p, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// 3x3 conv2d with a single input channel on the feature map (the stem of the 2-D backbones):
-//   F.relu(bn1(conv1(x.unsqueeze(1))))  campplus.py:284, resnet_se.py:131-133, eres2net.py:243
-// in: feats [B, T, F] (one channel), out: [B, T, F, C] channel-last.  w: [C][kt][kf] (BN folded by the host), bias [C].
-// One thread per (b, t, f) position x 4 output channels; 9 taps cached in registers.
+// KTxKF (<= 7x7) strided conv2d with a single input channel on the feature map (the stem of the 2-D backbones):
+//   F.relu(bn1(conv1(x.unsqueeze(1))))  campplus.py:284, resnet_se.py:131-133, eres2net.py:243 (3x3, stride 1) and
+//   res2net.py:100 (7x7, stride 3, padding 1)
+// in: feats [B, T, F] (one channel), out: [B, T', F', C] channel-last.  w: [C][kt][kf] (BN folded by the host), bias [C].
+// One thread per output position x 4 output channels.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_c1_kernel(const __grid_constant__ ConvParams p) {
   const int groups = p.N >> 2;
   const long long total = (long long)p.M * groups;
+  const int taps = p.KT * p.KF;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(idx % groups);
     const int m = (int)(idx / groups);
     RowInfo r = decode_row(p, m);
-    float x[9];
-#pragma unroll
-    for (int kt = 0; kt < 3; ++kt)
-#pragma unroll
-      for (int kf = 0; kf < 3; ++kf) {
-        int ti = r.t0 + kt, fi = r.f0 + kf;
-        bool ok = ti >= 0 && ti < p.Tin && fi >= 0 && fi < p.Fin;
-        x[kt * 3 + kf] = ok ? __ldg(p.src + ((size_t)r.base + (size_t)ti * p.Fin + fi) * p.in_ld + p.in_coff) : 0.f;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const float* w0 = p.w + (size_t)(g * 4) * p.w_ld;
+    for (int kt = 0; kt < p.KT; ++kt) {
+      const int ti = r.t0 + kt * p.dT;
+      if (ti < 0 || ti >= p.Tin) continue;
+      for (int kf = 0; kf < p.KF; ++kf) {
+        const int fi = r.f0 + kf * p.dF;
+        if (fi < 0 || fi >= p.Fin) continue;
+        const float x = __ldg(p.src + ((size_t)r.base + (size_t)ti * p.Fin + fi) * p.in_ld + p.in_coff);
+        const int k = kt * p.KF + kf;
+        a0 = fmaf(x, __ldg(w0 + k), a0);
+        a1 = fmaf(x, __ldg(w0 + p.w_ld + k), a1);
+        a2 = fmaf(x, __ldg(w0 + 2 * p.w_ld + k), a2);
+        a3 = fmaf(x, __ldg(w0 + 3 * p.w_ld + k), a3);
       }
-    float o[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int n = g * 4 + c;
-      const float* wr = p.w + (size_t)n * p.w_ld;
-      float a = 0.f;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) a = fmaf(x[k], __ldg(wr + k), a);
-      o[c] = epilogue1(p, a, m, n, urow_of(p, m));
     }
-    *reinterpret_cast<float4*>(p.dst + (size_t)m * p.out_ld + p.out_coff + g * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    (void)taps;
+    const int urow = urow_of(p, m);
+    const int n = g * 4;
+    *reinterpret_cast<float4*>(p.dst + (size_t)m * p.out_ld + p.out_coff + n) =
+        make_float4(epilogue1(p, a0, m, n, urow), epilogue1(p, a1, m, n + 1, urow), epilogue1(p, a2, m, n + 2, urow),
+                    epilogue1(p, a3, m, n + 3, urow));
   }
 }
 

@@ -31,6 +31,12 @@ struct EwParams {
   int x_ld, x_coff, y_ld, y_coff, att_ld, att_coff, res_ld, res_coff, out_ld, out_coff, mode, act2;
 };
 
+struct PoolParams {
+  const float* src; float* dst;
+  int B, Tin, Fin, Tout, Fout, C, in_ld, in_coff, out_ld, out_coff, KT, KF, sT, sF, padT, padF, mode;
+};
+cudaError_t launch_pool2d(const PoolParams& p, cudaStream_t stream);
+
 cudaError_t launch_frontend(const FrontendParams& p, const int* keep, cudaStream_t stream);
 cudaError_t launch_conv_ffma(const ConvParams& p, cudaStream_t stream);
 cudaError_t launch_conv_c1(const ConvParams& p, cudaStream_t stream);

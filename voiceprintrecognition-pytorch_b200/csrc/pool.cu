@@ -276,4 +276,46 @@ cudaError_t launch_ew(const EwParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// KTxKF pooling on a channel-last [B, T, F, C] map (column window in/out), float4 over channels.
+//   mode 0: nn.MaxPool2d(k, stride, padding)                      (res2net.py:105)
+//   mode 1: nn.AvgPool2d(k, stride, padding), count_include_pad   (res2net.py:33-34: divide by KT*KF always)
+__global__ void __launch_bounds__(256) pool2d_kernel(const __grid_constant__ PoolParams p) {
+  const int c4n = p.C >> 2;
+  const long long total = (long long)p.B * p.Tout * p.Fout * c4n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4n) * 4;
+    long long m = i / c4n;
+    const int fo = (int)(m % p.Fout);
+    m /= p.Fout;
+    const int to = (int)(m % p.Tout);
+    const int b = (int)(m / p.Tout);
+    float4 acc = p.mode == 0 ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kt = 0; kt < p.KT; ++kt) {
+      const int ti = to * p.sT - p.padT + kt;
+      if (ti < 0 || ti >= p.Tin) continue;
+      for (int kf = 0; kf < p.KF; ++kf) {
+        const int fi = fo * p.sF - p.padF + kf;
+        if (fi < 0 || fi >= p.Fin) continue;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p.src + ((size_t)(b * p.Tin + ti) * p.Fin + fi) * p.in_ld + p.in_coff + c));
+        if (p.mode == 0) { acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w); }
+        else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+      }
+    }
+    if (p.mode == 1) {
+      const float inv = 1.f / (float)(p.KT * p.KF);
+      acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    }
+    *reinterpret_cast<float4*>(p.dst + ((size_t)(b * p.Tout + to) * p.Fout + fo) * p.out_ld + p.out_coff + c) = acc;
+  }
+}
+
+cudaError_t launch_pool2d(const PoolParams& p, cudaStream_t stream) {
+  long long total = (long long)p.B * p.Tout * p.Fout * (p.C >> 2);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (blocks < 1) blocks = 1;
+  pool2d_kernel<<<(int)blocks, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
 }  // namespace vpb

@@ -7,7 +7,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libvpb200.so')
 
 VP_OK, VP_ERR_INVALID, VP_ERR_CUDA, VP_ERR_NOMEM, VP_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
-OP_CONV, OP_CONV_C1, OP_COLSTATS, OP_ASP_POOL, OP_EW = 1, 2, 3, 4, 5
+OP_CONV, OP_CONV_C1, OP_COLSTATS, OP_ASP_POOL, OP_EW, OP_POOL2D = 1, 2, 3, 4, 5, 6
+POOL_MAX, POOL_AVG = 0, 1
 ACT_NONE, ACT_RELU, ACT_HARDTANH20, ACT_SIGMOID, ACT_TANH, ACT_SILU = 0, 1, 2, 3, 4, 5
 PAD_ZERO, PAD_REFLECT = 0, 1
 SRC2_NONE, SRC2_ADD, SRC2_CONCAT = 0, 1, 2

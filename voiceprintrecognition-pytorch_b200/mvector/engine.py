@@ -293,6 +293,18 @@ class PlanBuilder:
         self.ops.append(o)
         return o
 
+    def pool2d(self, src, dst, mode, Tin, Fin, Tout, Fout, k=3, stride=1, pad=1):
+        o = self._new(L.OP_POOL2D)
+        o.mode = mode
+        o.src, o.in_ld, o.in_coff, o.Cin = src.off, src.ld, src.coff, src.C
+        o.dst, o.out_ld, o.out_coff = dst.off, dst.ld, dst.coff
+        o.Tin, o.Fin, o.Tout, o.Fout = Tin, Fin, Tout, Fout
+        o.KT = o.KF = k
+        o.sT = o.sF = stride
+        o.padT = o.padF = pad
+        self.ops.append(o)
+        return o
+
     def ew(self, mode, x, dst, rows_per_utt, gate=None, res=None, y=None, att=None, act2=L.ACT_NONE):
         o = self._new(L.OP_EW)
         o.mode = mode
