@@ -102,6 +102,9 @@ CASES = {
                                       pooling_type='ASP'), MEL64, [16000, 12000]),
     'eres2net_wide_small': ('ERes2Net', dict(embd_dim=32, num_blocks=[1, 1, 1, 1], m_channels=8, mul_channel=2,
                                              expansion=4, base_width=32, scale=3), FBANK24, [12000]),
+    # base_width 26 -> group widths 3, 6, 13, 26: none a multiple of 4, exercises the mirror's channel padding
+    'eres2netv2_small': ('ERes2NetV2', dict(embd_dim=32, num_blocks=[1, 1, 2, 1], m_channels=8, base_width=26, scale=2),
+                         FBANK24, [14400, 9000]),
 }
 
 
@@ -196,10 +199,11 @@ def main():
         'ERes2Net': (80, dict(embd_dim=192, m_channels=32)),
         'ERes2Net55M': (80, dict(embd_dim=192, m_channels=64, mul_channel=2, expansion=4, base_width=24, scale=3)),
         'Res2Net': (80, dict(embd_dim=192, pooling_type='ASP', m_channels=32)),
+        'ERes2NetV2': (80, dict(embd_dim=192, m_channels=32)),
     }
     digests = {}
     for key, (fdim, margs) in defaults.items():
-        model = 'ERes2Net' if key.startswith('ERes2Net') else key
+        model = 'ERes2Net' if key in ('ERes2Net', 'ERes2Net55M') else key
         cfg = dict_to_object({'model_conf': {'model': model, 'model_args': margs}})
         rsd = build_model(fdim, cfg).state_dict()
         s = ';'.join(f'{k}:{tuple(v.shape)}' for k, v in rsd.items())

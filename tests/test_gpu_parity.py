@@ -101,7 +101,7 @@ def test_frontend_loud_errors():
 
 # ------------------------------------------------------------------------------------------------ backbones
 SMALL = ['ecapa_small', 'tdnn_small', 'campplus_small', 'resnetse_small', 'eres2net_small', 'eres2net_wide_small',
-         'ecapa_sap_small', 'tdnn_tsp_small', 'resnetse_tap_small', 'res2net_small']
+         'ecapa_sap_small', 'tdnn_tsp_small', 'resnetse_tap_small', 'res2net_small', 'eres2netv2_small']
 
 
 @pytest.mark.parametrize('name', SMALL)
@@ -135,6 +135,7 @@ FULL = [
     ('ERes2Net', dict(embd_dim=192, m_channels=32), 80, 2, 130),
     ('ERes2Net', dict(embd_dim=192, m_channels=64, mul_channel=2, expansion=4, base_width=24, scale=3), 80, 1, 98),
     ('Res2Net', dict(embd_dim=192, pooling_type='ASP', m_channels=32), 80, 3, 298),
+    ('ERes2NetV2', dict(embd_dim=192, m_channels=32), 80, 2, 130),
 ]
 
 

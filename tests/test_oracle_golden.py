@@ -11,7 +11,7 @@ from oracle import frontend as fe
 from oracle import models as om
 
 SMALL = ['ecapa_small', 'tdnn_small', 'campplus_small', 'resnetse_small', 'eres2net_small', 'eres2net_wide_small',
-         'ecapa_sap_small', 'tdnn_tsp_small', 'resnetse_tap_small', 'res2net_small']
+         'ecapa_sap_small', 'tdnn_tsp_small', 'resnetse_tap_small', 'res2net_small', 'eres2netv2_small']
 
 
 @pytest.mark.parametrize('name', SMALL)
@@ -65,7 +65,7 @@ def test_param_shape_digests(manifest):
     """oracle.param_shapes enumerates exactly the reference's state_dict (names, order, shapes) at the
     default / BASELINE configurations."""
     for key, d in manifest['_param_digests'].items():
-        model = 'ERes2Net' if key.startswith('ERes2Net') else key
+        model = 'ERes2Net' if key in ('ERes2Net', 'ERes2Net55M') else key
         shapes = om.param_shapes(model, d['input_size'], **d['model_args'])
         s = ';'.join(f'{k}:{tuple(v)}' for k, v in shapes.items())
         assert hashlib.sha256(s.encode()).hexdigest() == d['sha256'], key
