@@ -58,6 +58,11 @@ def install_yeaudio_stub():
         def resample(self, sr):
             raise NotImplementedError
 
+        def crop(self, duration, mode='eval'):
+            # yeaudio is absent here; eval-mode crop keeps the leading `duration` seconds (train mode is random)
+            assert mode != 'train'
+            self.samples = self.samples[:int(duration * self.sample_rate)]
+
         def normalize(self, target_db=-20, max_gain_db=300.0):
             rms_db = 10.0 * np.log10(np.mean(self.samples.astype(np.float64) ** 2))
             gain = target_db - rms_db
@@ -69,6 +74,18 @@ def install_yeaudio_stub():
     mod.audio = sub
     sys.modules['yeaudio'] = mod
     sys.modules['yeaudio.audio'] = sub
+    # import-only stand-ins for what mvector/trainer.py and reader.py pull in but the eval path never calls
+    aug = types.ModuleType('yeaudio.augmentation')
+    for nm in ('ReverbPerturbAugmentor', 'SpecAugmentor', 'SpeedPerturbAugmentor', 'VolumePerturbAugmentor',
+               'NoisePerturbAugmentor'):
+        setattr(aug, nm, type(nm, (), {}))
+    sys.modules['yeaudio.augmentation'] = aug
+    ti = types.ModuleType('torchinfo')
+    ti.summary = lambda *a, **k: None
+    sys.modules['torchinfo'] = ti
+    vd = types.ModuleType('visualdl')
+    vd.LogWriter = type('LogWriter', (), {})
+    sys.modules['visualdl'] = vd
     return AudioSegment
 
 
@@ -189,6 +206,82 @@ def main():
                                         note='weights = oracle.models.random_state_dict(TDNN, 80, seed=7); '
                                              'dB-normalised to -20 dB by the yeaudio stub')
     print('c1 sim', sim)
+
+    # ---- evaluate caller (trainer.py:403-485) + metrics (metric/metrics.py) on a tiny 3-speaker wav set ----
+    import mvector.trainer as ref_trainer
+    eargs = dict(embd_dim=32, channels=64, pooling_type='ASP')
+    esd = om.random_state_dict('TDNN', 80, seed=21, **eargs)
+    rng = np.random.RandomState(5)
+    spk_f = [(180.0, 900.0), (260.0, 1500.0), (330.0, 2300.0)]
+
+    def spk_wave(spk, n, seed):
+        t = np.arange(n, dtype=np.float64) / 16000.0
+        f1, f2 = spk_f[spk]
+        w = 0.2 * np.sin(2 * np.pi * f1 * t) + 0.15 * np.sin(2 * np.pi * f2 * t) \
+            + 0.05 * np.random.RandomState(seed).randn(n)
+        return np.clip(w * 20000, -32767, 32767).astype(np.int16)
+
+    ev = {}
+    with tempfile.TemporaryDirectory() as td:
+        lists = {}
+        for nm, count in (('enroll', 6), ('trials', 9)):
+            lines = []
+            for i in range(count):
+                spk = i % 3
+                n = int(rng.randint(6400, 24000))            # 0.4 .. 1.5 s; eval max_duration 1.2 s crops the longest
+                pcm = spk_wave(spk, n, 50 * len(lines) + (0 if nm == 'enroll' else 1000) + i)
+                path = os.path.join(td, f'{nm}_{i}.wav')
+                with wave.open(path, 'wb') as w:
+                    w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000); w.writeframes(pcm.tobytes())
+                ev[f'{nm}_pcm{i}'] = pcm
+                ev[f'{nm}_label{i}'] = np.int32(spk)
+                lines.append(f'{path}\t{spk}\n')
+            lists[nm] = os.path.join(td, f'{nm}_list.txt')
+            with open(lists[nm], 'w') as f:
+                f.writelines(lines)
+        ecfg = base_config('TDNN', eargs, FBANK80)
+        ecfg['dataset_conf'].update(enroll_list=lists['enroll'], trials_list=lists['trials'],
+                                    dataLoader={'num_workers': 0})
+        ecfg['dataset_conf']['eval_conf'] = {'batch_size': 4, 'max_duration': 1.2}
+        ecfg['dataset_conf']['dataset']['use_dB_normalization'] = True
+        ecfg['train_conf'] = {'use_compile': False}
+        mdir = os.path.join(td, 'model')
+        os.makedirs(mdir)
+        torch.save({'0.' + k: v for k, v in esd.items()}, os.path.join(mdir, 'model.pth'))
+        captured = {}
+        real_fnr_fpr = ref_trainer.compute_fnr_fpr
+
+        def spy(scores, labels, weights=None):
+            captured['scores'], captured['labels'] = scores.copy(), labels.copy()
+            out = real_fnr_fpr(scores, labels, weights)
+            captured['fnr'], captured['fpr'], captured['thresholds'] = out
+            return out
+
+        ref_trainer.compute_fnr_fpr = spy
+        tr = ref_trainer.MVectorTrainer(configs=ecfg, use_gpu=False)
+        eer, min_dcf, thr = tr.evaluate(resume_model=mdir)
+        ref_trainer.compute_fnr_fpr = real_fnr_fpr
+    ev.update(eer=np.float64(eer), min_dcf=np.float64(min_dcf), threshold=np.float64(thr),
+              scores=captured['scores'], labels=captured['labels'], fnr=captured['fnr'], fpr=captured['fpr'],
+              thresholds=captured['thresholds'])
+    ev.update({'sd/' + k: v.numpy() for k, v in esd.items()})
+    np.savez_compressed(os.path.join(HERE, 'evaluate_small.npz'), **ev)
+    manifest['evaluate_small'] = dict(model='TDNN', model_args=eargs, preprocess=FBANK80, seed=21, n_enroll=6, n_trials=9,
+                                      eval_conf={'batch_size': 4, 'max_duration': 1.2},
+                                      note='reference MVectorTrainer.evaluate on CPU; yeaudio stubbed (normalize to '
+                                           '-20 dB, eval crop = leading max_duration seconds)')
+    print('evaluate', eer, min_dcf, thr)
+    # metrics alone, on a larger random score list with ties
+    from mvector.metric.metrics import compute_fnr_fpr, compute_eer, compute_dcf
+    mr = np.random.RandomState(11)
+    lab = (mr.rand(4000) < 0.2).astype(np.int32)
+    sc = np.round((mr.randn(4000) * 0.25 + lab * 0.45).astype(np.float32), 3)
+    fnr, fpr, th = compute_fnr_fpr(sc, lab)
+    m_eer, m_thr = compute_eer(fnr, fpr, sc)
+    np.savez_compressed(os.path.join(HERE, 'metrics.npz'), scores=sc, labels=lab, fnr=fnr, fpr=fpr, thresholds=th,
+                        eer=np.float64(m_eer), threshold=np.float64(m_thr), min_dcf=np.float64(compute_dcf(fnr, fpr)),
+                        min_dcf_05=np.float64(compute_dcf(fnr, fpr, p_target=0.05, c_miss=10, c_fa=1)))
+    manifest['metrics'] = dict(n=4000, note='mvector.metric.metrics on seeded random scores (rounded: ties present)')
 
     # ---- default-config parameter-name/shape digests, for checking oracle.param_shapes on the GPU box ----
     defaults = {

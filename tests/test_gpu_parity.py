@@ -410,3 +410,51 @@ def test_extract_features_npy_cache(tmp_path):
     ref = ofe.featurize(seg.samples, None, 'Fbank', fargs)[0].numpy()
     got = np.load(out[0].split('\t')[0])
     assert got.shape == ref.shape and np.abs(got - ref).max() < FBANK_ABS_TOL
+
+
+def test_evaluate_matches_reference_golden(tmp_path, manifest):
+    """MVectorTrainer.evaluate (trainer.py:403-485) on the 3-speaker wav set that the REFERENCE's
+    own evaluate was run on (tests/golden/evaluate_small.npz): same eval-order score list (duration sort, singly
+    featurized, feature-level zero padding per batch of 4) and the same EER / minDCF / threshold."""
+    from mvector.trainer import MVectorTrainer
+    import mvector.trainer as mt
+    m = manifest['evaluate_small']
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'evaluate_small.npz'))
+    lists = {}
+    for nm, count in (('enroll', m['n_enroll']), ('trials', m['n_trials'])):
+        lines = []
+        for i in range(count):
+            p = tmp_path / f'{nm}_{i}.wav'
+            with wave.open(str(p), 'wb') as w:
+                w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+                w.writeframes(z[f'{nm}_pcm{i}'].astype('<i2').tobytes())
+            lines.append(f'{p}\t{int(z[f"{nm}_label{i}"])}\n')
+        lp = tmp_path / f'{nm}_list.txt'
+        lp.write_text(''.join(lines))
+        lists[nm] = str(lp)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('sd/')}
+    mdir = tmp_path / 'model'
+    mdir.mkdir()
+    torch.save({'0.' + k: v for k, v in sd.items()}, str(mdir / 'model.pth'))
+    cfg = {'dataset_conf': {'dataset': {'min_duration': 0.3, 'max_duration': 3, 'sample_rate': 16000,
+                                        'use_dB_normalization': True, 'target_dB': -20},
+                            'eval_conf': dict(m['eval_conf']), 'enroll_list': lists['enroll'],
+                            'trials_list': lists['trials']},
+           'preprocess_conf': {'feature_method': 'Fbank', 'method_args': dict(m['preprocess']['method_args'])},
+           'model_conf': {'model': m['model'], 'model_args': dict(m['model_args'])}}
+    captured = {}
+    real = mt.compute_fnr_fpr
+
+    def spy(scores, labels, weights=None):
+        captured['scores'], captured['labels'] = scores.copy(), labels.copy()
+        return real(scores, labels, weights)
+
+    mt.compute_fnr_fpr = spy
+    try:
+        eer, min_dcf, thr = MVectorTrainer(cfg, use_gpu=True).evaluate(resume_model=str(mdir))
+    finally:
+        mt.compute_fnr_fpr = real
+    assert np.array_equal(captured['labels'], z['labels'])
+    assert np.abs(captured['scores'] - z['scores']).max() < 2e-5          # cosine scores, embeddings within 1e-4 rel-L2
+    assert abs(eer - float(z['eer'])) < 1e-6 and abs(min_dcf - float(z['min_dcf'])) < 1e-6
+    assert abs(thr - float(z['threshold'])) < 2e-5

@@ -175,3 +175,89 @@ def test_host_gather_pad_native():
             assert np.array_equal(dst[i, :len(w)], w) and not dst[i, len(w):].any()
     bad = (C.c_int32 * len(ws))(*([lmax + 1] + lens[1:]))
     assert L.lib().vp_host_gather_pad(ptrs, bad, len(ws), lmax, dst.ctypes.data_as(C.c_void_p), 2) == L.VP_ERR_INVALID
+
+
+def test_metrics_match_reference_golden():
+    """mvector.metric.metrics (metrics.py:5-39) against outputs of the reference's own functions on seeded scores with
+    ties (tests/golden/metrics.npz): fnr / fpr / thresholds bit-exact, EER / threshold / minDCF to 1e-12."""
+    from mvector.metric.metrics import compute_dcf, compute_eer, compute_fnr_fpr
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'metrics.npz'))
+    fnr, fpr, th = compute_fnr_fpr(z['scores'], z['labels'])
+    assert np.array_equal(fnr, z['fnr']) and np.array_equal(fpr, z['fpr']) and np.array_equal(th, z['thresholds'])
+    eer, thr = compute_eer(fnr, fpr, z['scores'])
+    assert abs(eer - float(z['eer'])) < 1e-12 and float(thr) == float(z['threshold'])
+    assert abs(compute_eer(fnr, fpr) - float(z['eer'])) < 1e-12
+    assert abs(compute_dcf(fnr, fpr) - float(z['min_dcf'])) < 1e-12
+    assert abs(compute_dcf(fnr, fpr, p_target=0.05, c_miss=10, c_fa=1) - float(z['min_dcf_05'])) < 1e-12
+
+
+def test_evaluate_scoring_matches_reference_golden():
+    """The score list the reference's evaluate built (trainer.py:452-468, captured by make_golden.py) -> same EER /
+    minDCF / threshold through the mirror's metric functions."""
+    from mvector.metric.metrics import compute_dcf, compute_eer, compute_fnr_fpr
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'evaluate_small.npz'))
+    fnr, fpr, _ = compute_fnr_fpr(z['scores'], z['labels'])
+    eer, thr = compute_eer(fnr, fpr, z['scores'])
+    assert abs(float(eer) - float(z['eer'])) < 1e-12 and float(thr) == float(np.float32(z['threshold']))
+    assert abs(float(compute_dcf(fnr, fpr)) - float(z['min_dcf'])) < 1e-12
+
+
+def test_evaluate_host_logic_with_oracle_backend(tmp_path, manifest):
+    """evaluate's list handling (duration sort, single-utterance featurize, eval crop, feature-level padding per batch,
+    trial-major scoring) checked on CPU: the device pieces (featurizer, backbone) are swapped for the oracle, the
+    result must reproduce what the reference's evaluate produced (tests/golden/evaluate_small.npz)."""
+    import mvector.trainer as mt
+    from oracle import frontend as ofe, models as om
+    from mvector.utils.utils import dict_to_object
+    m = manifest['evaluate_small']
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'evaluate_small.npz'))
+    lists = {}
+    for nm, count in (('enroll', m['n_enroll']), ('trials', m['n_trials'])):
+        lines = []
+        for i in range(count):
+            p = tmp_path / f'{nm}_{i}.wav'
+            with wave.open(str(p), 'wb') as w:
+                w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+                w.writeframes(z[f'{nm}_pcm{i}'].astype('<i2').tobytes())
+            lines.append(f'{p}\t{int(z[f"{nm}_label{i}"])}\n')
+        (tmp_path / f'{nm}_list.txt').write_text(''.join(lines))
+        lists[nm] = str(tmp_path / f'{nm}_list.txt')
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('sd/')}
+    fargs = dict(m['preprocess']['method_args'])
+
+    class Fz:
+        def __call__(self, w):
+            return ofe.featurize(w.numpy(), None, 'Fbank', fargs)
+
+        def num_frames(self, n):
+            return 1 + (n - 400) // 160
+
+    class Net:
+        def eval(self):
+            return self
+
+        def __call__(self, x):
+            return om.forward(m['model'], sd, x, **m['model_args'])
+
+    tr = object.__new__(mt.MVectorTrainer)
+    tr.configs = dict_to_object({'dataset_conf': {'dataset': {'sample_rate': 16000, 'use_dB_normalization': True,
+                                                              'target_dB': -20},
+                                                  'eval_conf': dict(m['eval_conf']), 'enroll_list': lists['enroll'],
+                                                  'trials_list': lists['trials']}})
+    tr.use_gpu, tr.stop_eval, tr._device = False, False, torch.device('cpu')
+    tr.audio_featurizer, tr.model = Fz(), Net()
+    captured = {}
+    real = mt.compute_fnr_fpr
+
+    def spy(scores, labels, weights=None):
+        captured['scores'], captured['labels'] = scores.copy(), labels.copy()
+        return real(scores, labels, weights)
+
+    mt.compute_fnr_fpr = spy
+    try:
+        eer, min_dcf, thr = tr.evaluate()
+    finally:
+        mt.compute_fnr_fpr = real
+    assert np.array_equal(captured['labels'], z['labels'])
+    assert np.abs(captured['scores'] - z['scores']).max() < 2e-6
+    assert abs(eer - float(z['eer'])) < 1e-9 and abs(min_dcf - float(z['min_dcf'])) < 1e-9

@@ -1,11 +1,20 @@
-"""MVectorTrainer -- only the hot-path caller ``extract_features`` (reference: mvector/trainer.py:146-175) is provided.
+"""MVectorTrainer -- the two hot-path callers: ``extract_features`` (reference: mvector/trainer.py:146-175) and
+``evaluate`` (trainer.py:403-485).
 
 ``extract_features`` walks the train / enroll / trials lists (``path\\tlabel`` lines), runs the front-end on every file
 exactly like ``MVectorDataset.__getitem__`` does in ``mode='extract_feature'`` (reader.py:82-107: skip files shorter than
 ``min_duration``, resample, dB-normalise, crop to ``max_duration`` from the start, featurize ONE utterance -> [T, F]) and
 writes the reference's feature cache: ``<save_dir>/<label>/<ms timestamp>.npy`` float32 [T, F] plus a
 ``*_features.txt`` list that the reference's reader consumes (reader.py:76-81).  The front-end runs on the fused sm_100a
-kernel.  Training / evaluation / export are outside the embedding-extraction path and raise."""
+kernel.
+
+``evaluate`` embeds the enroll and trials lists and scores every trial against every enrolment.  Data semantics follow
+``MVectorDataset(mode='eval')`` + ``collate_fn`` (reader.py:63-109,127-144; collate_fn.py:5-24): lists are sorted by
+duration (``np.argsort``), every file is featurized ALONE (CMN over its own frames, no mask), cropped from the start to
+``eval_conf.max_duration``, then ``eval_conf.batch_size`` consecutive features are zero-padded at the FEATURE level to
+the longest in the batch and fed to the backbone -- padded frames do reach the pooling layer, exactly as in the
+reference.  Front-end and backbone run on the sm_100a kernels; the score matrix / EER / minDCF are numpy glue
+(trainer.py:452-468, metric/metrics.py).  Training and export are outside the embedding-extraction path and raise."""
 import os
 import time
 
@@ -16,6 +25,7 @@ from loguru import logger
 
 from .audio import AudioSegment
 from .data_utils.featurizer import AudioFeaturizer
+from .metric.metrics import compute_dcf, compute_eer, compute_fnr_fpr
 from .utils.utils import dict_to_object, print_arguments
 
 
@@ -30,7 +40,10 @@ class MVectorTrainer(object):
                 configs = yaml.load(f.read(), Loader=yaml.FullLoader)
             print_arguments(configs=configs)
         self.configs = dict_to_object(configs)
+        self.use_gpu = use_gpu
         self.audio_featurizer = None
+        self.model = None
+        self.stop_eval = False
 
     def extract_features(self, save_dir='dataset/features', max_duration=100):
         """提取特征保存文件 (trainer.py:146-175)"""
@@ -84,8 +97,111 @@ class MVectorTrainer(object):
     def train(self, *args, **kwargs):
         raise NotImplementedError('training is outside the B200 embedding-extraction path (SURVEY.md section 2, row 7)')
 
-    def evaluate(self, *args, **kwargs):
-        raise NotImplementedError('evaluate (trainer.py:403-485) is a SURVEY.md 8(f) "next" row, not lowered yet')
+    # ------------------------------------------------------------------ evaluate (trainer.py:403-485)
+    def _setup_eval(self):
+        from .engine import Engine
+        from .models import build_model
+        pc = self.configs.preprocess_conf
+        self._engine = Engine(torch.cuda.current_device())
+        self._device = self._engine.device
+        self.audio_featurizer = AudioFeaturizer(feature_method=pc.feature_method,
+                                                use_hf_model=pc.get('use_hf_model', False),
+                                                method_args=pc.get('method_args', {}), engine=self._engine)
+        self.model = build_model(input_size=self.audio_featurizer.feature_dim, configs=self.configs)
+        self.model.engine = self._engine
+
+    def _eval_items(self, data_list):
+        """Features of one list in the reference's eval order: [(feature [T, F] on the device, label)]."""
+        ds = self.configs.dataset_conf.get('dataset', {})
+        sample_rate = ds.get('sample_rate', 16000)
+        use_db, target_db = ds.get('use_dB_normalization', True), ds.get('target_dB', -20)
+        max_duration = self.configs.dataset_conf.eval_conf.max_duration          # trainer.py:126
+        # get_crop_feature_len (reader.py:119-124): frames of a max_duration-long waveform
+        max_feature_len = self.audio_featurizer.num_frames(int(max_duration * sample_rate))
+        with open(data_list, 'r', encoding='utf-8') as f:
+            lines = f.readlines()
+        loaded, lengths = [], []
+        for line in lines:                                                       # sort_list, reader.py:127-144
+            path, label = line.replace('\n', '').split('\t')
+            if path.endswith('.npy'):
+                obj = np.load(path)
+                lengths.append(obj.shape[0])
+            else:
+                obj = AudioSegment.from_file(path)
+                lengths.append(obj.duration)
+            loaded.append((path, int(label), obj))
+        items = []
+        for i in np.argsort(lengths):
+            path, label, obj = loaded[i]
+            if path.endswith('.npy'):                                            # reader.py:76-81
+                feature = torch.from_numpy(np.asarray(obj[:max_feature_len], dtype=np.float32)).to(self._device)
+            else:
+                seg = obj
+                if seg.sample_rate != sample_rate:
+                    seg.resample(sample_rate)
+                if use_db:
+                    seg.normalize(target_db=target_db)
+                if seg.duration > max_duration:                                  # crop(mode='eval'): from the start
+                    seg.samples = seg.samples[:int(max_duration * seg.sample_rate)]
+                feature = self.audio_featurizer(torch.from_numpy(seg.samples)).squeeze(0)
+            items.append((feature, label))
+        return items
+
+    def _embed_list(self, data_list):
+        items = self._eval_items(data_list)
+        bs = self.configs.dataset_conf.eval_conf.batch_size
+        feats, labels = [], []
+        for s in range(0, len(items), bs):
+            if self.stop_eval:
+                break
+            chunk = items[s:s + bs]
+            tmax = max(f.shape[0] for f, _ in chunk)
+            x = torch.zeros((len(chunk), tmax, chunk[0][0].shape[1]), dtype=torch.float32, device=self._device)
+            for i, (f, _) in enumerate(chunk):                                   # collate_fn.py:12-19
+                x[i, :f.shape[0]] = f
+            feats.append(self.model(x).cpu().numpy())
+            labels.extend(lb for _, lb in chunk)
+        return np.concatenate(feats), np.asarray(labels, dtype=np.int32)
+
+    def evaluate(self, resume_model=None, save_image_path=None):
+        """评估模型 (trainer.py:403-485) -> (eer, min_dcf, threshold)"""
+        from .utils.checkpoint import load_pretrained
+        if self.model is None:
+            self._setup_eval()
+        if resume_model is not None:
+            if os.path.isdir(resume_model):
+                resume_model = os.path.join(resume_model, 'model.pth')
+            assert os.path.exists(resume_model), f"{resume_model} 模型不存在！"
+            self.model = load_pretrained(self.model, resume_model, use_gpu=self.use_gpu)
+        self.model.eval()
+        enroll_features, enroll_labels = self._embed_list(self.configs.dataset_conf.enroll_list)
+        trials_features, trials_labels = self._embed_list(self.configs.dataset_conf.trials_list)
+        if self.stop_eval:
+            return -1, -1, -1
+        logger.info('开始对比音频特征...')
+        # cosine_similarity of every trial against every enrolment (trainer.py:454-461), trial-major order
+        en = enroll_features / np.linalg.norm(enroll_features, axis=1, keepdims=True)
+        tn = trials_features / np.linalg.norm(trials_features, axis=1, keepdims=True)
+        all_score = (tn @ en.T).astype(np.float32).reshape(-1)
+        all_labels = (trials_labels[:, None] == enroll_labels[None, :]).astype(np.int32).reshape(-1)
+        fnr, fpr, thresholds = compute_fnr_fpr(all_score, all_labels)
+        eer, threshold = compute_eer(fnr, fpr, all_score)
+        min_dcf = compute_dcf(fnr, fpr)
+        eer, min_dcf, threshold = float(eer), float(min_dcf), float(threshold)
+        if save_image_path:                                                       # trainer.py:471-484
+            import matplotlib.pyplot as plt
+            at = int(np.flatnonzero(np.asarray(thresholds) == threshold)[0])
+            plt.plot(thresholds, fnr, color='blue', linestyle='-', label='fnr')
+            plt.plot(thresholds, fpr, color='red', linestyle='-', label='fpr')
+            plt.plot(threshold, fpr[at], 'ro-')
+            plt.text(threshold, fpr[at], (round(threshold, 3), round(fpr[at], 5)), color='red')
+            plt.xlabel('threshold')
+            plt.title('fnr and fpr')
+            plt.grid(True)
+            os.makedirs(save_image_path, exist_ok=True)
+            plt.savefig(os.path.join(save_image_path, 'result.png'))
+            logger.info(f"结果图以保存在：{os.path.join(save_image_path, 'result.png')}")
+        return eer, min_dcf, threshold
 
     def export(self, *args, **kwargs):
         raise NotImplementedError('torch.jit export does not apply to the C-ABI path')
