@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define VP_ABI_VERSION 1
+#define VP_ABI_VERSION 2
 
 enum {
   VP_OK = 0,
@@ -49,15 +49,19 @@ typedef struct vp_program vp_program;
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct vp_frontend_desc {
   int32_t kind;         /* 0 kaldi-fbank framing, 1 centred-STFT framing */
-  int32_t n_fft;        /* FFT size, power of two in [256, 2048] */
+  int32_t n_fft;        /* FFT size N = 2^a 3^b 5^c, multiple of 4, in [64, 2048]; kind 0 needs a power of two */
   int32_t win_length;   /* samples taken per frame (<= n_fft); window[] has this many taps */
   int32_t hop;          /* frame shift in samples */
-  int32_t n_mels;       /* output feature dimension F (<= 128) */
+  int32_t n_mels;       /* filter count: <= 128 mel filters, or n_fft/2+1 (<= 1025) pass-through bins for Spectrogram */
   int32_t remove_dc;    /* kind 0: subtract the frame mean */
   float   preemph;      /* kind 0: pre-emphasis coefficient (0 = off) */
   int32_t power;        /* 2 = power spectrum, 1 = magnitude */
-  int32_t use_log;      /* 1: log(max(mel, log_floor)) */
+  int32_t use_log;      /* 0 none; 1 ln(max(x, log_floor)); 2 db_mult*log10(max(x, log_floor)); 3 ln(x + log_floor) */
   float   log_floor;
+  int32_t post;         /* 0: the filter outputs are the features; 1: MFCC = DCT-II over the n_mels log values */
+  int32_t n_out;        /* post 1: cepstral coefficients kept (<= n_mels); ignored otherwise */
+  float   db_mult;      /* use_log 2 multiplier (10 for power, AmplitudeToDB) */
+  float   top_db;       /* post 1: clamp the log values to (max over the whole call) - top_db first; < 0 = no clamp */
 } vp_frontend_desc;
 
 int vp_create(int device, vp_handle** out);
@@ -68,20 +72,30 @@ int32_t vp_sizeof_op(void);             /* binding self-check: sizeof(vp_op) */
 int32_t vp_sizeof_frontend_desc(void);  /* binding self-check: sizeof(vp_frontend_desc) */
 
 /* window: win_length floats.  Mel bank in CSR-like form: filter m covers FFT bins
- * [mel_start[m], mel_start[m] + mel_count[m]) with weights mel_w[mel_off[m] ...]; all host pointers, copied. */
+ * [mel_start[m], mel_start[m] + mel_count[m]) with weights mel_w[mel_off[m] ...]; dct: [n_mels, n_out] row-major
+ * (torchaudio create_dct layout) when desc->post == 1, else NULL; all host pointers, copied. */
 int vp_frontend_set(vp_handle* h, const vp_frontend_desc* desc, const float* window, const int32_t* mel_start,
-                    const int32_t* mel_count, const int32_t* mel_off, const float* mel_w, int32_t n_w);
+                    const int32_t* mel_count, const int32_t* mel_off, const float* mel_w, int32_t n_w, const float* dct);
+/* feature dimension F the configured front-end emits (n_mels, or n_out for MFCC) */
+int32_t vp_feature_dim(const vp_handle* h);
 /* number of frames T the configured front-end yields for n_samples (kaldi.py:63-67 / torch.stft) */
 int32_t vp_num_frames(const vp_handle* h, int32_t n_samples);
 
 /* wave [B, Lpad] (zero padded to the batch max, predict.py:248-254) -> feats [B, T, F], T = vp_num_frames(Lpad).
  * keep_frames: device int32 [B] = round(len_i / Lmax * T) (featurizer.py:82-84) or NULL for no masking.
- * scratch: device floats, at least vp_frontend_scratch_floats(B, Lpad).  vp_fbank requires kind 0, vp_melspec kind 1. */
+ * scratch: device floats, at least vp_frontend_scratch_floats(B, Lpad).
+ * vp_fbank   = torchaudio.compliance.kaldi.fbank per utterance (featurizer.py:47-48,119-132): kind 0, post 0.
+ * vp_melspec = torchaudio.transforms.MelSpectrogram, and Spectrogram with a pass-through bank (featurizer.py:41-44):
+ *              kind 1, post 0.
+ * vp_mfcc    = torchaudio.transforms.MFCC (featurizer.py:45-46): kind 1, post 1.  The top_db clamp uses the maximum
+ *              over ALL B utterances of the call, as torchaudio does for a [B, n_mels, T] input. */
 size_t vp_frontend_scratch_floats(const vp_handle* h, int32_t B, int32_t Lpad);
 int vp_fbank(vp_handle* h, const float* wave, int32_t B, int32_t Lpad, const int32_t* keep_frames, float* feats,
              float* scratch, void* stream);
 int vp_melspec(vp_handle* h, const float* wave, int32_t B, int32_t Lpad, const int32_t* keep_frames, float* feats,
                float* scratch, void* stream);
+int vp_mfcc(vp_handle* h, const float* wave, int32_t B, int32_t Lpad, const int32_t* keep_frames, float* feats,
+            float* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Backbone (seam 2).  The host (Python mirror of mvector/models/*.py) lowers a model + a concrete (B, T) to a
@@ -109,7 +123,8 @@ enum {                       /* VP_OP_COLSTATS modes (op.mode) */
   VP_STATS_SEG_CONTEXT = 4,        /* out[b, s, c] = mean over rows + mean over segment s (ceil)  (campplus.py:96-111) */
   VP_STATS_MEAN_VAR_UNBIASED = 5   /* [mean ; sum((x-mean)^2)/(R-1)]  (TemporalStatisticsPooling returns the VARIANCE, pooling.py:44-46) */
 };
-enum { VP_EW_GATE_RES = 0, VP_EW_AFF = 1, VP_EW_COPY = 2 };
+enum { VP_EW_GATE_RES = 0, VP_EW_AFF = 1, VP_EW_COPY = 2,
+       VP_EW_PAD_COPY = 3 };  /* dst[r, 0:Cout] = (src[r, 0:Cin], zeros): any Cin / in_ld; Cout % 4 == 0 (odd feature dims) */
 enum { VP_BUF_NONE = -1, VP_BUF_INPUT = -2, VP_BUF_OUTPUT = -3 };  /* special values for activation offsets */
 enum { VP_ENGINE_AUTO = 0, VP_ENGINE_FFMA = 1, VP_ENGINE_TC = 2 }; /* vp_op.engine: which conv kernel family */
 

@@ -4,6 +4,8 @@ TEST INFRASTRUCTURE (see oracle/__init__.py).  Restates, in this repo's own word
   * torchaudio.compliance.kaldi.fbank            (kaldi.py:514-645; framing :44-83, window :154-217,
                                                   mel banks :436-511)
   * torchaudio.transforms.MelSpectrogram          (functional.py:52-144 spectrogram, :518-587 melscale_fbanks)
+  * torchaudio.transforms.Spectrogram / MFCC      (transforms: Spectrogram.forward, MFCC.forward; functional.py:352-403
+                                                  amplitude_to_DB, :640-667 create_dct)
   * mvector AudioFeaturizer.forward               (mvector/data_utils/featurizer.py:53-91)
   * mvector KaldiFbank.forward per-utterance loop (mvector/data_utils/featurizer.py:119-132)
 """
@@ -172,23 +174,94 @@ def htk_mel_fbanks(n_freqs, f_min, f_max, n_mels, sample_rate):
     return torch.max(torch.zeros(1), torch.min(down, up))                       # functional.py:507-513
 
 
+def _power_stft(w, n_fft, win, hop, power, pad=0):
+    """functional.spectrogram (functional.py:52-144) for center=True, reflect, onesided, not normalized."""
+    w = torch.as_tensor(w, dtype=torch.float32)
+    if pad > 0:
+        w = torch.nn.functional.pad(w, (pad, pad))
+    window = torch.hann_window(win)                                             # periodic hann, transforms:62
+    spec = torch.stft(w, n_fft=n_fft, hop_length=hop, win_length=win, window=window, center=True,
+                      pad_mode='reflect', normalized=False, onesided=True, return_complex=True)
+    return spec.abs() if power == 1.0 else spec.abs().pow(power)                # functional.py:139-142
+
+
 def mel_spectrogram(waveforms, **kwargs):
     """waveforms [B, L] -> [B, n_mels, T]  (no log: featurizer.py:76 uses the raw transform)."""
     a = melspec_args(**kwargs)
     if a['mel_scale'] != 'htk' or a['norm'] is not None or a['normalized'] or a['pad_mode'] != 'reflect' \
             or not a['center']:
         raise NotImplementedError('oracle melspec: unsupported option')
-    w = torch.as_tensor(waveforms, dtype=torch.float32)
-    if a['pad'] > 0:
-        w = torch.nn.functional.pad(w, (a['pad'], a['pad']))
-    n_fft, win, hop = a['n_fft'], a['win_length'], a['hop_length']
-    window = torch.hann_window(win)                                             # periodic hann, transforms:62
-    spec = torch.stft(w, n_fft=n_fft, hop_length=hop, win_length=win, window=window, center=True,
-                      pad_mode='reflect', normalized=False, onesided=True, return_complex=True)
-    p = a['power']
-    spec = spec.abs() if p == 1.0 else spec.abs().pow(p)                        # functional.py:139-142
-    fb = htk_mel_fbanks(n_fft // 2 + 1, a['f_min'], a['f_max'], a['n_mels'], a['sample_rate'])
+    spec = _power_stft(waveforms, a['n_fft'], a['win_length'], a['hop_length'], a['power'], a['pad'])
+    fb = htk_mel_fbanks(a['n_fft'] // 2 + 1, a['f_min'], a['f_max'], a['n_mels'], a['sample_rate'])
     return torch.matmul(spec.transpose(-1, -2), fb).transpose(-1, -2)          # MelScale.forward
+
+
+_SPEC_KEYS = dict(n_fft=400, win_length=None, hop_length=None, pad=0, power=2.0, normalized=False, center=True,
+                  pad_mode='reflect', onesided=True)
+
+
+def spectrogram(waveforms, **kwargs):
+    """torchaudio.transforms.Spectrogram as built by featurizer.py:43-44: waveforms [B, L] -> [B, n_fft//2+1, T]."""
+    for k in kwargs:
+        if k not in _SPEC_KEYS:
+            raise TypeError(f"Spectrogram.__init__() got an unexpected keyword argument '{k}'")
+    a = dict(_SPEC_KEYS)
+    a.update(kwargs)
+    win = a['win_length'] if a['win_length'] is not None else a['n_fft']
+    hop = a['hop_length'] if a['hop_length'] is not None else win // 2
+    if a['normalized'] or a['pad_mode'] != 'reflect' or not a['center'] or not a['onesided'] or a['power'] is None:
+        raise NotImplementedError('oracle spectrogram: unsupported option')
+    return _power_stft(waveforms, a['n_fft'], win, hop, a['power'], a['pad'])
+
+
+_MFCC_KEYS = dict(sample_rate=16000, n_mfcc=40, dct_type=2, norm='ortho', log_mels=False, melkwargs=None)
+
+
+def dct_matrix(n_mfcc, n_mels, norm):
+    """functional.create_dct (functional.py:640-667): DCT-II basis, returned [n_mels, n_mfcc]."""
+    n = torch.arange(float(n_mels))
+    k = torch.arange(float(n_mfcc)).unsqueeze(1)
+    dct = torch.cos(math.pi / float(n_mels) * (n + 0.5) * k)
+    if norm is None:
+        dct *= 2.0
+    else:
+        assert norm == 'ortho'
+        dct[0] *= 1.0 / math.sqrt(2.0)
+        dct *= math.sqrt(2.0 / float(n_mels))
+    return dct.t()
+
+
+def power_to_db(x, top_db=80.0, amin=1e-10):
+    """AmplitudeToDB('power', top_db) (functional.amplitude_to_DB, functional.py:352-403) with ref 1.0: 10*log10(max(x,
+    amin)); the top_db clamp folds a 3-D input's leading (batch) axis into the channel axis, so ONE maximum is shared
+    by the whole batch."""
+    x_db = 10.0 * torch.log10(torch.clamp(x, min=amin))
+    x_db -= 10.0 * math.log10(max(amin, 1.0))
+    if top_db is not None:
+        shape = x_db.size()
+        packed = shape[-3] if x_db.dim() > 2 else 1
+        x4 = x_db.reshape(-1, packed, shape[-2], shape[-1])
+        x4 = torch.max(x4, (x4.amax(dim=(-3, -2, -1)) - top_db).view(-1, 1, 1, 1))
+        x_db = x4.reshape(shape)
+    return x_db
+
+
+def mfcc(waveforms, **kwargs):
+    """torchaudio.transforms.MFCC as built by featurizer.py:45-46: waveforms [B, L] -> [B, n_mfcc, T]."""
+    for k in kwargs:
+        if k not in _MFCC_KEYS:
+            raise TypeError(f"MFCC.__init__() got an unexpected keyword argument '{k}'")
+    a = dict(_MFCC_KEYS)
+    a.update(kwargs)
+    if a['dct_type'] != 2:
+        raise ValueError('DCT type not supported: {}'.format(a['dct_type']))
+    mk = dict(a['melkwargs'] or {})
+    mel = mel_spectrogram(waveforms, sample_rate=a['sample_rate'], **mk)
+    n_mels = mel.shape[-2]
+    if a['n_mfcc'] > n_mels:
+        raise ValueError('Cannot select more MFCC coefficients than # mel bins')
+    mel = torch.log(mel + 1e-6) if a['log_mels'] else power_to_db(mel)
+    return torch.matmul(mel.transpose(-1, -2), dct_matrix(a['n_mfcc'], n_mels, a['norm'])).transpose(-1, -2)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -205,6 +278,10 @@ def featurize(waveforms, input_lens_ratio=None, feature_method='Fbank', method_a
         feat = kaldi_fbank_batch(w, **method_args)
     elif feature_method == 'MelSpectrogram':
         feat = mel_spectrogram(w, **method_args)
+    elif feature_method == 'Spectrogram':
+        feat = spectrogram(w, **method_args)
+    elif feature_method == 'MFCC':
+        feat = mfcc(w, **method_args)
     else:
         raise Exception(f'预处理方法 {feature_method} 不存在!')
     feat = feat.transpose(2, 1)
@@ -224,6 +301,10 @@ def feature_dim(feature_method, method_args):
         return method_args.get('n_mels', 128)
     if feature_method == 'Fbank':
         return method_args.get('num_mel_bins', 23)
+    if feature_method == 'Spectrogram':
+        return method_args.get('n_fft', 400) // 2 + 1
+    if feature_method == 'MFCC':
+        return method_args.get('n_mfcc', 40)
     raise Exception('没有{}预处理方法'.format(feature_method))
 
 

@@ -98,6 +98,11 @@ MEL64 = dict(feature_method='MelSpectrogram',
              method_args=dict(sample_rate=16000, n_fft=1024, win_length=1024, hop_length=320, f_min=50.0,
                               f_max=14000.0, n_mels=64))
 
+SPEC400 = dict(feature_method='Spectrogram', method_args=dict())                      # torchaudio defaults: n_fft 400 -> 201 bins
+MFCC24 = dict(feature_method='MFCC', method_args=dict(n_mfcc=24, melkwargs=dict(n_fft=512, hop_length=160, n_mels=64,
+                                                                                 f_min=20.0)))
+MFCC40 = dict(feature_method='MFCC', method_args=dict())                              # defaults: n_fft 400, 128 mels, 40 coeffs
+
 # name -> (model, model_args, preprocess, lengths in samples)
 CASES = {
     'ecapa_small': ('EcapaTdnn', dict(embd_dim=32, pooling_type='ASP', channels=[64, 64, 64, 64, 192],
@@ -122,6 +127,14 @@ CASES = {
     # base_width 26 -> group widths 3, 6, 13, 26: none a multiple of 4, exercises the mirror's channel padding
     'eres2netv2_small': ('ERes2NetV2', dict(embd_dim=32, num_blocks=[1, 1, 2, 1], m_channels=8, base_width=26, scale=2),
                          FBANK24, [14400, 9000]),
+    # Spectrogram / MFCC front-ends (featurizer.py:43-46); 201 input features exercise the 1-D models' input padding,
+    # n_fft = 400 the radix-5 FFT passes, the ragged MFCC batch the call-wide top_db clamp
+    'tdnn_spec_small': ('TDNN', dict(embd_dim=32, channels=64, pooling_type='ASP'), SPEC400, [9600, 8000]),
+    'resnetse_mfcc_small': ('ResNetSE', dict(embd_dim=32, layers=[1, 1, 1, 1], num_filters=[16, 16, 32, 32],
+                                             pooling_type='ASP'), MFCC24, [12000, 11000, 5600]),
+    'ecapa_mfcc400_small': ('EcapaTdnn', dict(embd_dim=32, pooling_type='ASP', channels=[64, 64, 64, 64, 192],
+                                              attention_channels=32, res2net_scale=4, se_channels=16), MFCC40,
+                            [9000, 6400]),
 }
 
 

@@ -167,6 +167,9 @@ class Sim:
         rpu = o.Tin * o.Fin
         rows = o.B * rpu
         v = self.rd(o.src, rows, o.in_ld, o.in_coff, o.Cin)
+        if o.mode == L.EW_PAD_COPY:
+            self.wr(o.dst, rows, o.out_ld, o.out_coff, o.Cout, np.pad(v, ((0, 0), (0, o.Cout - o.Cin))))
+            return
         if o.mode == L.EW_GATE_RES:
             if o.gate != L.BUF_NONE:
                 v = v * self.rd(o.gate, o.B, o.Cin, 0, o.Cin)[np.arange(rows) // rpu]

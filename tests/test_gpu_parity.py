@@ -87,13 +87,63 @@ def test_melspectrogram(margs):
     assert ((got - ref).abs().max() / ref.abs().max()).item() < 2e-6
 
 
+@pytest.mark.parametrize('method,margs', [
+    ('MelSpectrogram', dict()),                                              # torchaudio defaults: n_fft 400 (radix-5 passes)
+    ('Spectrogram', dict()),                                                 # 201 pass-through bins
+    ('Spectrogram', dict(n_fft=512, hop_length=160, power=1.0)),
+    ('Spectrogram', dict(n_fft=480, win_length=400)),                        # radix-3 pass, short window centred in n_fft
+])
+def test_stft_frontends_mixed_radix(method, margs):
+    """Spectrogram (featurizer.py:43-44) and non-power-of-two n_fft through the same fused kernel."""
+    from oracle import frontend as ofe
+    g = torch.Generator().manual_seed(6)
+    waves = [(torch.randn(n, generator=g) * 0.1).numpy() for n in (16000, 12345, 4000)]
+    x, ratio = ofe.pad_batch(waves)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref = ofe.featurize(x, ratio, method, margs)
+    fz = _featurizer(dict(feature_method=method, method_args=margs))
+    got = fz(torch.from_numpy(x), torch.from_numpy(ratio)).cpu()
+    assert got.shape == ref.shape and got.shape[2] == fz.feature_dim
+    assert ((got - ref).abs().max() / ref.abs().max()).item() < 3e-6
+    one = fz(torch.from_numpy(waves[1])).cpu()
+    ref1 = ofe.featurize(waves[1], None, method, margs)
+    assert ((one - ref1).abs().max() / ref1.abs().max()).item() < 3e-6
+
+
+@pytest.mark.parametrize('margs', [
+    dict(),                                                                  # n_fft 400, 128 mels, 40 coefficients, top_db 80
+    dict(n_mfcc=24, melkwargs=dict(n_fft=512, hop_length=160, n_mels=64, f_min=20.0)),
+    dict(log_mels=True, norm=None, melkwargs=dict(n_fft=512, n_mels=40)),
+])
+def test_mfcc(margs):
+    """torchaudio.transforms.MFCC (featurizer.py:45-46): dB with the call-wide top_db clamp (the quiet third utterance
+    is clamped by the loud ones' maximum), DCT-II, then CMN + mask."""
+    from oracle import frontend as ofe
+    g = torch.Generator().manual_seed(7)
+    waves = [(torch.randn(n, generator=g) * a).numpy() for n, a in ((16000, 0.1), (12345, 0.3), (9000, 1e-5))]
+    x, ratio = ofe.pad_batch(waves)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref = ofe.featurize(x, ratio, 'MFCC', margs)
+        ref1 = ofe.featurize(waves[2], None, 'MFCC', margs)
+    fz = _featurizer(dict(feature_method='MFCC', method_args=margs))
+    got = fz(torch.from_numpy(x), torch.from_numpy(ratio)).cpu()
+    assert got.shape == ref.shape
+    assert ((got - ref).abs().max() / ref.abs().max()).item() < 2e-5
+    one = fz(torch.from_numpy(waves[2])).cpu()                               # alone, the quiet utterance is NOT clamped
+    assert ((one - ref1).abs().max() / ref1.abs().max()).item() < 2e-5
+
+
 def test_frontend_loud_errors():
     from mvector._lib import VpError
     fz = _featurizer(dict(feature_method='Fbank', method_args=dict(sample_frequency=16000, num_mel_bins=80)))
     with pytest.raises(AssertionError):
         fz(torch.zeros(1, 300))                     # shorter than one frame: reference asserts too (kaldi.py:141)
     with pytest.raises(NotImplementedError):
-        _featurizer(dict(feature_method='MelSpectrogram', method_args=dict(n_fft=400)))
+        _featurizer(dict(feature_method='MelSpectrogram', method_args=dict(n_fft=442)))     # 2 * 13 * 17
     with pytest.raises(TypeError):
         _featurizer(dict(feature_method='Fbank', method_args=dict(n_mels=80)))
     assert VpError is not None
@@ -101,7 +151,8 @@ def test_frontend_loud_errors():
 
 # ------------------------------------------------------------------------------------------------ backbones
 SMALL = ['ecapa_small', 'tdnn_small', 'campplus_small', 'resnetse_small', 'eres2net_small', 'eres2net_wide_small',
-         'ecapa_sap_small', 'tdnn_tsp_small', 'resnetse_tap_small', 'res2net_small', 'eres2netv2_small']
+         'ecapa_sap_small', 'tdnn_tsp_small', 'resnetse_tap_small', 'res2net_small', 'eres2netv2_small', 'tdnn_spec_small',
+         'resnetse_mfcc_small', 'ecapa_mfcc400_small']
 
 
 @pytest.mark.parametrize('name', SMALL)

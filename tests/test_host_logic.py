@@ -25,7 +25,7 @@ def test_cabi_library_exports_every_declared_symbol():
     from mvector import _lib
     assert set(_lib.EXPORTS) == declared
     L = _lib.lib()
-    assert L.vp_abi_version() == 1
+    assert L.vp_abi_version() == 2
     assert L.vp_sizeof_op() == ctypes.sizeof(_lib.Op)
 
 
@@ -101,8 +101,16 @@ def test_featurizer_surface():
     assert fz.keep_frames([0.5], 297).tolist() == [148]
     with pytest.raises(TypeError):
         AudioFeaturizer('Fbank', method_args=dict(bogus=1))
+    # torchaudio defaults (n_fft = 400, a 2^4 5^2 FFT) are accepted for all three STFT front-ends
+    assert AudioFeaturizer('MFCC').feature_dim == 40 and AudioFeaturizer('Spectrogram').feature_dim == 201
+    assert AudioFeaturizer('MelSpectrogram').feature_dim == 128
+    assert AudioFeaturizer('Spectrogram', method_args=dict(n_fft=512)).num_frames(16000) == 1 + 16000 // 256
     with pytest.raises(NotImplementedError):
-        AudioFeaturizer('MFCC')
+        AudioFeaturizer('Spectrogram', method_args=dict(n_fft=442))          # 442 = 2 * 13 * 17
+    with pytest.raises(ValueError):
+        AudioFeaturizer('MFCC', method_args=dict(n_mfcc=200))
+    with pytest.raises(NotImplementedError):
+        AudioFeaturizer('Fbank', use_hf_model=True)
     with pytest.raises(Exception):
         AudioFeaturizer('Nope')
 

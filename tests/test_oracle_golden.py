@@ -11,7 +11,8 @@ from oracle import frontend as fe
 from oracle import models as om
 
 SMALL = ['ecapa_small', 'tdnn_small', 'campplus_small', 'resnetse_small', 'eres2net_small', 'eres2net_wide_small',
-         'ecapa_sap_small', 'tdnn_tsp_small', 'resnetse_tap_small', 'res2net_small', 'eres2netv2_small']
+         'ecapa_sap_small', 'tdnn_tsp_small', 'resnetse_tap_small', 'res2net_small', 'eres2netv2_small', 'tdnn_spec_small',
+         'resnetse_mfcc_small', 'ecapa_mfcc400_small']
 
 
 @pytest.mark.parametrize('name', SMALL)

@@ -27,6 +27,7 @@ struct vp_handle {
   int* d_mel_count = nullptr;
   int* d_mel_off = nullptr;
   float* d_mel_w = nullptr;
+  float* d_dct = nullptr;
 };
 
 struct vp_program {
@@ -82,7 +83,8 @@ int vp_create(int device, vp_handle** out) {
 
 static void free_frontend(vp_handle* h) {
   cudaFree(h->d_window); cudaFree(h->d_twiddle); cudaFree(h->d_mel_start); cudaFree(h->d_mel_count);
-  cudaFree(h->d_mel_off); cudaFree(h->d_mel_w);
+  cudaFree(h->d_mel_off); cudaFree(h->d_mel_w); cudaFree(h->d_dct);
+  h->d_dct = nullptr;
   h->d_window = nullptr; h->d_twiddle = nullptr; h->d_mel_start = h->d_mel_count = h->d_mel_off = nullptr;
   h->d_mel_w = nullptr;
   h->fe_set = false;
@@ -99,15 +101,27 @@ void vp_destroy(vp_handle* h) {
 const char* vp_last_error(const vp_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
 int vp_frontend_set(vp_handle* h, const vp_frontend_desc* d, const float* window, const int32_t* mel_start,
-                    const int32_t* mel_count, const int32_t* mel_off, const float* mel_w, int32_t n_w) {
+                    const int32_t* mel_count, const int32_t* mel_off, const float* mel_w, int32_t n_w, const float* dct) {
   if (!h || !d || !window || !mel_start || !mel_count || !mel_off || !mel_w) return fail(h, VP_ERR_INVALID, "null argument");
   const int N = d->n_fft;
-  if (N < 256 || N > 2048 || (N & (N - 1))) return fail(h, VP_ERR_UNSUPPORTED, "n_fft %d: need a power of two in [256, 2048]", N);
+  int rem = N > 0 ? N : 1;
+  for (int f : {2, 3, 5}) while (rem % f == 0) rem /= f;
+  if (N < 64 || N > 2048 || (N & 3) || rem != 1)
+    return fail(h, VP_ERR_UNSUPPORTED, "n_fft %d: need 2^a 3^b 5^c, a multiple of 4, in [64, 2048]", N);
   if (d->kind != 0 && d->kind != 1) return fail(h, VP_ERR_INVALID, "front-end kind %d", d->kind);
+  if (d->kind == 0 && (N & (N - 1))) return fail(h, VP_ERR_UNSUPPORTED, "kaldi framing needs a power-of-two n_fft");
   if (d->win_length < 2 || d->win_length > N || d->hop < 1) return fail(h, VP_ERR_INVALID, "bad window/hop");
   if (d->kind == 1 && d->win_length != N) return fail(h, VP_ERR_INVALID, "stft framing needs a window of n_fft taps");
-  if (d->n_mels < 1 || d->n_mels > 128) return fail(h, VP_ERR_UNSUPPORTED, "n_mels %d > 128", d->n_mels);
+  if (d->n_mels < 1 || d->n_mels > N / 2 + 1) return fail(h, VP_ERR_UNSUPPORTED, "n_mels %d out of range", d->n_mels);
   if (d->power != 1 && d->power != 2) return fail(h, VP_ERR_UNSUPPORTED, "power must be 1 or 2");
+  if (d->use_log < 0 || d->use_log > 3) return fail(h, VP_ERR_INVALID, "use_log %d", d->use_log);
+  if (d->post != 0 && d->post != 1) return fail(h, VP_ERR_INVALID, "post %d", d->post);
+  if (d->post == 1) {
+    if (d->kind != 1) return fail(h, VP_ERR_UNSUPPORTED, "MFCC needs stft framing");
+    if (!dct) return fail(h, VP_ERR_INVALID, "MFCC needs the DCT matrix");
+    if (d->n_mels > 128 || d->n_out < 1 || d->n_out > d->n_mels)
+      return fail(h, VP_ERR_UNSUPPORTED, "MFCC: n_mels %d (<= 128), n_out %d (<= n_mels)", d->n_mels, d->n_out);
+  }
   for (int m = 0; m < d->n_mels; ++m) {
     if (mel_count[m] < 0 || mel_start[m] < 0 || mel_start[m] + mel_count[m] > N / 2 + 1 || mel_off[m] < 0 ||
         mel_off[m] + mel_count[m] > n_w)
@@ -133,6 +147,10 @@ int vp_frontend_set(vp_handle* h, const vp_frontend_desc* d, const float* window
   CUDA_TRY(h, cudaMemcpy(h->d_mel_count, mel_count, sizeof(int) * F, cudaMemcpyHostToDevice));
   CUDA_TRY(h, cudaMemcpy(h->d_mel_off, mel_off, sizeof(int) * F, cudaMemcpyHostToDevice));
   if (n_w > 0) CUDA_TRY(h, cudaMemcpy(h->d_mel_w, mel_w, sizeof(float) * n_w, cudaMemcpyHostToDevice));
+  if (d->post == 1) {
+    CUDA_TRY(h, cudaMalloc(&h->d_dct, sizeof(float) * F * d->n_out));
+    CUDA_TRY(h, cudaMemcpy(h->d_dct, dct, sizeof(float) * F * d->n_out, cudaMemcpyHostToDevice));
+  }
   h->fe = *d;
   h->fe_set = true;
   return VP_OK;
@@ -144,18 +162,30 @@ int32_t vp_num_frames(const vp_handle* h, int32_t n) {
   return 1 + n / h->fe.hop;
 }
 
+int32_t vp_feature_dim(const vp_handle* h) {
+  if (!h || !h->fe_set) return -1;
+  return h->fe.post == 1 ? h->fe.n_out : h->fe.n_mels;
+}
+
+static size_t round4(size_t n) { return (n + 3) & ~(size_t)3; }
+
+// scratch layout: [CMN partial sums B*nblk*F] and, for MFCC, [per-CTA maxima B*nblk] [dB mel values B*T*n_mels]
 size_t vp_frontend_scratch_floats(const vp_handle* h, int32_t B, int32_t Lpad) {
   int T = vp_num_frames(h, Lpad);
   if (T <= 0) return 0;
   size_t nblk = (T + FPB - 1) / FPB;
-  return (size_t)B * nblk * h->fe.n_mels;
+  size_t n = round4((size_t)B * nblk * vp_feature_dim(h));
+  if (h->fe.post == 1) n += round4((size_t)B * nblk) + round4((size_t)B * T * h->fe.n_mels);
+  return n;
 }
 
-static int run_frontend(vp_handle* h, int want_kind, const float* wave, int B, int L, const int32_t* keep,
+// want_kind / want_post: -1 = whatever is configured (vp_embed_wave)
+static int run_frontend(vp_handle* h, int want_kind, int want_post, const float* wave, int B, int L, const int32_t* keep,
                         float* feats, float* scratch, cudaStream_t st) {
   if (!h) return VP_ERR_INVALID;
   if (!h->fe_set) return fail(h, VP_ERR_INVALID, "front-end not configured (vp_frontend_set)");
   if (want_kind >= 0 && h->fe.kind != want_kind) return fail(h, VP_ERR_INVALID, "front-end kind mismatch");
+  if (want_post >= 0 && h->fe.post != want_post) return fail(h, VP_ERR_INVALID, "front-end post-stage mismatch (vp_melspec vs vp_mfcc)");
   if (!wave || !feats || !scratch || B < 1) return fail(h, VP_ERR_INVALID, "null/empty argument");
   const int T = vp_num_frames(h, L);
   if (T < 1) return fail(h, VP_ERR_INVALID, "waveform of %d samples is shorter than one frame (%d)", L, h->fe.win_length);
@@ -167,18 +197,33 @@ static int run_frontend(vp_handle* h, int want_kind, const float* wave, int B, i
   p.B = B; p.L = L; p.T = T; p.kind = h->fe.kind; p.N = h->fe.n_fft; p.WL = h->fe.win_length; p.hop = h->fe.hop;
   p.F = h->fe.n_mels; p.remove_dc = h->fe.remove_dc; p.power = h->fe.power; p.use_log = h->fe.use_log;
   p.fpb = FPB; p.nblk = (T + FPB - 1) / FPB;
-  p.preemph = h->fe.preemph; p.log_floor = h->fe.log_floor;
+  p.preemph = h->fe.preemph; p.log_floor = h->fe.log_floor; p.db_mult = h->fe.db_mult; p.cta_max = nullptr;
+  if (h->fe.post == 1) {
+    MfccParams m;
+    float* cta_max = scratch + round4((size_t)B * p.nblk * h->fe.n_out);
+    float* mel = cta_max + round4((size_t)B * p.nblk);
+    p.feats = mel; p.partial = nullptr; p.cta_max = cta_max;
+    m.mel = mel; m.cta_max = cta_max; m.dct = h->d_dct; m.feats = feats; m.partial = scratch;
+    m.B = B; m.T = T; m.M = h->fe.n_mels; m.K = h->fe.n_out; m.fpb = FPB; m.nblk = p.nblk; m.n_max = B * p.nblk;
+    m.top_db = h->fe.top_db;
+    CUDA_TRY(h, launch_frontend_mfcc(p, m, keep, st));
+    return VP_OK;
+  }
   CUDA_TRY(h, launch_frontend(p, keep, st));
   return VP_OK;
 }
 
 int vp_fbank(vp_handle* h, const float* wave, int32_t B, int32_t Lpad, const int32_t* keep, float* feats,
              float* scratch, void* stream) {
-  return run_frontend(h, 0, wave, B, Lpad, keep, feats, scratch, (cudaStream_t)stream);
+  return run_frontend(h, 0, 0, wave, B, Lpad, keep, feats, scratch, (cudaStream_t)stream);
 }
 int vp_melspec(vp_handle* h, const float* wave, int32_t B, int32_t Lpad, const int32_t* keep, float* feats,
                float* scratch, void* stream) {
-  return run_frontend(h, 1, wave, B, Lpad, keep, feats, scratch, (cudaStream_t)stream);
+  return run_frontend(h, 1, 0, wave, B, Lpad, keep, feats, scratch, (cudaStream_t)stream);
+}
+int vp_mfcc(vp_handle* h, const float* wave, int32_t B, int32_t Lpad, const int32_t* keep, float* feats,
+            float* scratch, void* stream) {
+  return run_frontend(h, 1, 1, wave, B, Lpad, keep, feats, scratch, (cudaStream_t)stream);
 }
 
 int vp_weights_load(vp_handle* h, const void* blob, size_t nbytes) {
@@ -321,6 +366,13 @@ static int validate_op(vp_program* p, const vp_op& o, int i) {
     }
     case VP_OP_EW: {
       const long long rows = (long long)o.B * o.Tin * o.Fin;
+      if (o.mode == VP_EW_PAD_COPY) {
+        if (rows < 1 || o.Cin < 1 || o.Cout < o.Cin || (o.Cout & 3) || (o.out_ld & 3) || (o.out_coff & 3))
+          return fail(h, VP_ERR_UNSUPPORTED, "op %d: PAD_COPY shape", i);
+        TRY(check_act_buf(p, "x", o.src, view_floats(rows, o.in_ld, o.in_coff, o.Cin), false, i));
+        TRY(check_act_buf(p, "dst", o.dst, view_floats(rows, o.out_ld, o.out_coff, o.Cout), true, i));
+        return VP_OK;
+      }
       if (rows < 1 || o.Cin < 4 || (o.Cin & 3) || (o.in_ld & 3) || (o.in_coff & 3) || (o.out_ld & 3) || (o.out_coff & 3))
         return fail(h, VP_ERR_UNSUPPORTED, "op %d: EW alignment", i);
       if (!act_ok(o.act2)) return fail(h, VP_ERR_INVALID, "op %d: activation id", i);
@@ -479,7 +531,7 @@ static int run_ops(vp_program* p, const float* feats, float* emb, cudaStream_t s
         e.rows = (long long)o.B * o.Tin * o.Fin; e.C = o.Cin; e.rows_per_utt = o.Tin * o.Fin;
         e.x_ld = o.in_ld; e.x_coff = o.in_coff; e.y_ld = o.src2_ld; e.y_coff = o.src2_coff;
         e.att_ld = o.res_ld; e.att_coff = o.res_coff; e.res_ld = o.res_ld; e.res_coff = o.res_coff;
-        e.out_ld = o.out_ld; e.out_coff = o.out_coff; e.mode = o.mode; e.act2 = o.act2;
+        e.out_ld = o.out_ld; e.out_coff = o.out_coff; e.mode = o.mode; e.act2 = o.act2; e.C_out = o.Cout;
         CUDA_TRY(h, launch_ew(e, st));
         break;
       }
@@ -532,9 +584,9 @@ int vp_program_op_info(const vp_program* p, int32_t i, int32_t* kind, int64_t* M
 int vp_embed_wave(vp_program* p, const float* wave, int32_t B, int32_t Lpad, const int32_t* keep, float* feats_scratch,
                   float* fe_scratch, float* emb, void* stream) {
   if (!p) return VP_ERR_INVALID;
-  int r = run_frontend(p->h, -1, wave, B, Lpad, keep, feats_scratch, fe_scratch, (cudaStream_t)stream);
+  int r = run_frontend(p->h, -1, -1, wave, B, Lpad, keep, feats_scratch, fe_scratch, (cudaStream_t)stream);
   if (r != VP_OK) return r;
-  const size_t need = (size_t)B * vp_num_frames(p->h, Lpad) * p->h->fe.n_mels;
+  const size_t need = (size_t)B * vp_num_frames(p->h, Lpad) * vp_feature_dim(p->h);
   if (need != p->in_floats) return fail(p->h, VP_ERR_INVALID, "program expects %zu input floats, front-end produced %zu", p->in_floats, need);
   return vp_embed(p, feats_scratch, emb, stream);
 }

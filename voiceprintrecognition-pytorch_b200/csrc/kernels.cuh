@@ -9,7 +9,15 @@ struct FrontendParams {
   const float* window; const float2* twiddle;
   const int* mel_start; const int* mel_count; const int* mel_off; const float* mel_w;
   int B, L, T, kind, N, WL, hop, F, remove_dc, power, use_log, fpb, nblk;
-  float preemph, log_floor;
+  float preemph, log_floor, db_mult;
+  float* cta_max;      // non-null: MFCC mel stage (per-CTA maxima instead of CMN partial sums)
+};
+
+// MFCC tail: mel [B,T,M] dB values -> clamp(max - top_db) -> DCT [M,K] -> feats [B,T,K] + CMN partial sums.
+struct MfccParams {
+  const float* mel; const float* cta_max; const float* dct; float* feats; float* partial;
+  int B, T, M, K, fpb, nblk, n_max;
+  float top_db;        // < 0: no clamp
 };
 
 struct StatsParams {
@@ -29,6 +37,7 @@ struct EwParams {
   const float* x; const float* y; const float* att; const float* gate; const float* res; float* dst;
   long long rows; int C, rows_per_utt;
   int x_ld, x_coff, y_ld, y_coff, att_ld, att_coff, res_ld, res_coff, out_ld, out_coff, mode, act2;
+  int C_out;   // PAD_COPY: destination width (>= C, zero filled)
 };
 
 struct PoolParams {
@@ -38,6 +47,8 @@ struct PoolParams {
 cudaError_t launch_pool2d(const PoolParams& p, cudaStream_t stream);
 
 cudaError_t launch_frontend(const FrontendParams& p, const int* keep, cudaStream_t stream);
+cudaError_t launch_frontend_mfcc(const FrontendParams& p, const MfccParams& m, const int* keep, cudaStream_t stream);
+size_t frontend_smem_bytes(int N, int WL, int hop, int fpb);
 cudaError_t launch_conv_ffma(const ConvParams& p, cudaStream_t stream);
 cudaError_t launch_conv_c1(const ConvParams& p, cudaStream_t stream);
 cudaError_t launch_colstats(const StatsParams& p, cudaStream_t stream);

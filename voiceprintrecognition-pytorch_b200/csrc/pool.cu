@@ -267,7 +267,23 @@ __global__ void __launch_bounds__(256) ew_kernel(const __grid_constant__ EwParam
   }
 }
 
+// dst[r, 0:C_out] = (x[r, 0:C], 0 ...): scalar, for feature dims that are not multiples of 4 (Spectrogram's n_fft/2+1 bins)
+__global__ void __launch_bounds__(256) pad_copy_kernel(const __grid_constant__ EwParams p) {
+  const long long total = p.rows * p.C_out;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / p.C_out;
+    const int c = (int)(i - m * p.C_out);
+    p.dst[m * p.out_ld + p.out_coff + c] = c < p.C ? __ldg(p.x + m * p.x_ld + p.x_coff + c) : 0.f;
+  }
+}
+
 cudaError_t launch_ew(const EwParams& p, cudaStream_t stream) {
+  if (p.mode == VP_EW_PAD_COPY) {
+    long long blocks = (p.rows * p.C_out + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    pad_copy_kernel<<<(int)(blocks < 1 ? 1 : blocks), 256, 0, stream>>>(p);
+    return cudaGetLastError();
+  }
   long long total = p.rows * (p.C >> 2);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;

@@ -14,7 +14,7 @@ PAD_ZERO, PAD_REFLECT = 0, 1
 SRC2_NONE, SRC2_ADD, SRC2_CONCAT = 0, 1, 2
 STATS_MEAN, STATS_MEAN_STD_CLAMP, STATS_MEAN_STD_UNBIASED, STATS_MEAN_STD_TSTP, STATS_SEG_CONTEXT = 0, 1, 2, 3, 4
 STATS_MEAN_VAR_UNBIASED = 5
-EW_GATE_RES, EW_AFF, EW_COPY = 0, 1, 2
+EW_GATE_RES, EW_AFF, EW_COPY, EW_PAD_COPY = 0, 1, 2, 3
 BUF_NONE, BUF_INPUT, BUF_OUTPUT = -1, -2, -3
 ENGINE_AUTO, ENGINE_FFMA, ENGINE_TC = 0, 1, 2
 
@@ -22,7 +22,8 @@ ENGINE_AUTO, ENGINE_FFMA, ENGINE_TC = 0, 1, 2
 class FrontendDesc(C.Structure):
     _fields_ = [('kind', C.c_int32), ('n_fft', C.c_int32), ('win_length', C.c_int32), ('hop', C.c_int32),
                 ('n_mels', C.c_int32), ('remove_dc', C.c_int32), ('preemph', C.c_float), ('power', C.c_int32),
-                ('use_log', C.c_int32), ('log_floor', C.c_float)]
+                ('use_log', C.c_int32), ('log_floor', C.c_float), ('post', C.c_int32), ('n_out', C.c_int32),
+                ('db_mult', C.c_float), ('top_db', C.c_float)]
 
 
 class Op(C.Structure):
@@ -65,11 +66,13 @@ def lib():
         'vp_destroy': (None, [vp]),
         'vp_last_error': (C.c_char_p, [vp]),
         'vp_frontend_set': (C.c_int, [vp, C.POINTER(FrontendDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                      C.c_void_p, i32]),
+                                      C.c_void_p, i32, C.c_void_p]),
+        'vp_feature_dim': (i32, [vp]),
         'vp_num_frames': (i32, [vp, i32]),
         'vp_frontend_scratch_floats': (sz, [vp, i32, i32]),
         'vp_fbank': (C.c_int, [vp, f32p, i32, i32, i32p, f32p, f32p, vp]),
         'vp_melspec': (C.c_int, [vp, f32p, i32, i32, i32p, f32p, f32p, vp]),
+        'vp_mfcc': (C.c_int, [vp, f32p, i32, i32, i32p, f32p, f32p, vp]),
         'vp_weights_load': (C.c_int, [vp, C.c_void_p, sz]),
         'vp_program_create': (C.c_int, [vp, C.POINTER(Op), i32, sz, sz, sz, pp]),
         'vp_program_destroy': (None, [vp]),
@@ -85,7 +88,7 @@ def lib():
         fn = getattr(L, name)          # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if L.vp_abi_version() != 1:
+    if L.vp_abi_version() != 2:
         raise RuntimeError('libvpb200.so ABI version mismatch')
     if L.vp_sizeof_op() != C.sizeof(Op) or L.vp_sizeof_frontend_desc() != C.sizeof(FrontendDesc):
         raise RuntimeError('vp_op / vp_frontend_desc layout mismatch between the ctypes binding and libvpb200.so')
@@ -94,6 +97,7 @@ def lib():
 
 
 EXPORTS = ['vp_abi_version', 'vp_sizeof_op', 'vp_sizeof_frontend_desc', 'vp_create', 'vp_destroy', 'vp_last_error',
-           'vp_frontend_set', 'vp_num_frames', 'vp_frontend_scratch_floats', 'vp_fbank', 'vp_melspec',
+           'vp_frontend_set', 'vp_num_frames', 'vp_frontend_scratch_floats', 'vp_fbank', 'vp_melspec', 'vp_mfcc',
+           'vp_feature_dim',
            'vp_weights_load', 'vp_program_create', 'vp_program_destroy', 'vp_embed', 'vp_embed_wave',
            'vp_program_launches', 'vp_program_peek', 'vp_embed_profiled', 'vp_program_op_info', 'vp_host_gather_pad']

@@ -1,8 +1,10 @@
 """AudioFeaturizer mirror (reference: mvector/data_utils/featurizer.py:9-132), backed by the fused sm_100a front-end.
 
-Host side only prepares constants once (window, sparse mel bank -- the reference rebuilds them on every call,
-kaldi.py:201,621-627) and hands device pointers to ``vp_fbank`` / ``vp_melspec``; the per-utterance Python loop
-(featurizer.py:124-131), the transpose, the CMN and the length mask (featurizer.py:77-90) all run in two kernels.
+Host side only prepares constants once (window, sparse mel bank, DCT matrix -- the reference rebuilds the Kaldi ones on
+every call, kaldi.py:201,621-627) and hands device pointers to ``vp_fbank`` / ``vp_melspec`` / ``vp_mfcc``; the
+per-utterance Python loop (featurizer.py:124-131), the transpose, the CMN and the length mask (featurizer.py:77-90) all
+run in two kernels (three for MFCC).  All four ``feature_method`` values of the reference are lowered: Fbank,
+MelSpectrogram, Spectrogram (pass-through bank over the n_fft/2+1 bins) and MFCC.
 """
 import ctypes as C
 import math
@@ -23,6 +25,28 @@ _FBANK_DEFAULTS = dict(blackman_coeff=0.42, channel=-1, dither=0.0, energy_floor
 _MELSPEC_DEFAULTS = dict(sample_rate=16000, n_fft=400, win_length=None, hop_length=None, f_min=0.0, f_max=None,
                          pad=0, n_mels=128, power=2.0, normalized=False, center=True, pad_mode='reflect',
                          onesided=None, norm=None, mel_scale='htk')
+_SPEC_DEFAULTS = dict(n_fft=400, win_length=None, hop_length=None, pad=0, power=2.0, normalized=False, center=True,
+                      pad_mode='reflect', onesided=True)
+_MFCC_DEFAULTS = dict(sample_rate=16000, n_mfcc=40, dct_type=2, norm='ortho', log_mels=False, melkwargs=None)
+
+
+def _fft_size_ok(n):
+    """The front-end FFT handles N = 2^a 3^b 5^c, 4 | N, 64 <= N <= 2048 (torchaudio's default n_fft = 400 included)."""
+    if n < 64 or n > 2048 or n % 4:
+        return False
+    for f in (2, 3, 5):
+        while n % f == 0:
+            n //= f
+    return n == 1
+
+
+def _stft_window(n_fft, win_length):
+    """Periodic Hann of win_length taps, centred inside n_fft like torch.stft does for a short window."""
+    win = torch.hann_window(win_length)
+    if win_length < n_fft:
+        left = (n_fft - win_length) // 2
+        win = torch.nn.functional.pad(win, (left, n_fft - win_length - left))
+    return win.numpy().astype(np.float32)
 
 
 def _sparse_bank(dense):
@@ -121,16 +145,13 @@ class MelSpectrogram:
                               ('normalized', bool(a['normalized'])), ('center', not a['center']),
                               ('pad_mode', a['pad_mode'] != 'reflect'), ('norm', a['norm'] is not None),
                               ('mel_scale', a['mel_scale'] != 'htk'), ('power', a['power'] not in (1.0, 2.0, 1, 2)),
-                              ('n_fft (power of two in [256, 2048])', n_fft < 256 or n_fft > 2048 or n_fft & (n_fft - 1)),
+                              ('n_fft (2^a 3^b 5^c, multiple of 4, in [64, 2048])', not _fft_size_ok(n_fft)),
+                              ('n_mels (<= 128)', a['n_mels'] > 128),
                               ('win_length', win_length > n_fft)) if b]
         if bad:
             raise NotImplementedError('MelSpectrogram options not lowered to the sm_100a front-end: ' + ', '.join(bad))
         self.n_fft, self.hop, self.n_mels = n_fft, hop, a['n_mels']
-        win = torch.hann_window(win_length)
-        if win_length < n_fft:                                  # torch.stft centres a short window inside n_fft
-            left = (n_fft - win_length) // 2
-            win = torch.nn.functional.pad(win, (left, n_fft - win_length - left))
-        self.window = win.numpy().astype(np.float32)
+        self.window = _stft_window(n_fft, win_length)
         self.win_length = n_fft
         n_freqs = n_fft // 2 + 1
         all_freqs = torch.linspace(0, a['sample_rate'] // 2, n_freqs)
@@ -143,12 +164,88 @@ class MelSpectrogram:
         self.bank = _sparse_bank(fb.T.contiguous().numpy())
         self.desc = L.FrontendDesc(kind=1, n_fft=n_fft, win_length=n_fft, hop=hop, n_mels=self.n_mels, remove_dc=0,
                                    preemph=0.0, power=int(a['power']), use_log=0, log_floor=0.0)
+        self.dct = None
+        self.n_out = self.n_mels
+
+
+class Spectrogram:
+    """kwargs of torchaudio.transforms.Spectrogram (featurizer.py:43-44): the MelSpectrogram pipeline without the mel
+    projection -- the "bank" is the identity over the n_fft/2+1 bins, so the same kernel emits |X|^power directly."""
+
+    def __init__(self, **kwargs):
+        for k in kwargs:
+            if k not in _SPEC_DEFAULTS and k not in ('window_fn', 'wkwargs'):
+                raise TypeError(f"Spectrogram.__init__() got an unexpected keyword argument '{k}'")
+        a = dict(_SPEC_DEFAULTS)
+        a.update(kwargs)
+        self.kwargs = kwargs
+        n_fft = a['n_fft']
+        win_length = a['win_length'] if a['win_length'] is not None else n_fft
+        hop = a['hop_length'] if a['hop_length'] is not None else win_length // 2
+        bad = [k for k, b in (('window_fn', 'window_fn' in kwargs or 'wkwargs' in kwargs), ('pad', a['pad'] != 0),
+                              ('normalized', bool(a['normalized'])), ('center', not a['center']),
+                              ('pad_mode', a['pad_mode'] != 'reflect'), ('onesided', not a['onesided']),
+                              ('power', a['power'] not in (1.0, 2.0, 1, 2)),
+                              ('n_fft (2^a 3^b 5^c, multiple of 4, in [64, 2048])', not _fft_size_ok(n_fft)),
+                              ('win_length', win_length > n_fft)) if b]
+        if bad:
+            raise NotImplementedError('Spectrogram options not lowered to the sm_100a front-end: ' + ', '.join(bad))
+        nb = n_fft // 2 + 1
+        self.n_fft, self.hop, self.n_mels = n_fft, hop, nb
+        self.window = _stft_window(n_fft, win_length)
+        self.win_length = n_fft
+        idx = np.arange(nb, dtype=np.int32)
+        self.bank = (idx, np.ones(nb, np.int32), idx.copy(), np.ones(nb, np.float32))
+        self.desc = L.FrontendDesc(kind=1, n_fft=n_fft, win_length=n_fft, hop=hop, n_mels=nb, remove_dc=0, preemph=0.0,
+                                   power=int(a['power']), use_log=0, log_floor=0.0)
+        self.dct = None
+        self.n_out = nb
+
+
+class MFCC:
+    """kwargs of torchaudio.transforms.MFCC (featurizer.py:45-46): MelSpectrogram(sample_rate, **melkwargs) ->
+    AmplitudeToDB('power', top_db=80) (or log(mel + 1e-6) when log_mels) -> DCT-II (create_dct, functional.py:640-667)."""
+
+    def __init__(self, **kwargs):
+        for k in kwargs:
+            if k not in _MFCC_DEFAULTS:
+                raise TypeError(f"MFCC.__init__() got an unexpected keyword argument '{k}'")
+        a = dict(_MFCC_DEFAULTS)
+        a.update(kwargs)
+        self.kwargs = kwargs
+        if a['dct_type'] != 2:
+            raise ValueError('DCT type not supported: {}'.format(a['dct_type']))
+        mel = MelSpectrogram(sample_rate=a['sample_rate'], **(a['melkwargs'] or {}))
+        n_mfcc, n_mels = a['n_mfcc'], mel.n_mels
+        if n_mfcc > n_mels:
+            raise ValueError('Cannot select more MFCC coefficients than # mel bins')
+        self.n_fft, self.hop, self.n_mels, self.win_length = mel.n_fft, mel.hop, n_mels, mel.win_length
+        self.window, self.bank = mel.window, mel.bank
+        n = torch.arange(float(n_mels))
+        k = torch.arange(float(n_mfcc)).unsqueeze(1)
+        dct = torch.cos(math.pi / float(n_mels) * (n + 0.5) * k)
+        if a['norm'] is None:
+            dct *= 2.0
+        else:
+            assert a['norm'] == 'ortho'
+            dct[0] *= 1.0 / math.sqrt(2.0)
+            dct *= math.sqrt(2.0 / float(n_mels))
+        self.dct = np.ascontiguousarray(dct.t().numpy(), dtype=np.float32)          # [n_mels, n_mfcc]
+        self.n_out = n_mfcc
+        if a['log_mels']:
+            self.desc = L.FrontendDesc(kind=1, n_fft=mel.n_fft, win_length=mel.n_fft, hop=mel.hop, n_mels=n_mels,
+                                       remove_dc=0, preemph=0.0, power=mel.desc.power, use_log=3, log_floor=1e-6,
+                                       post=1, n_out=n_mfcc, db_mult=0.0, top_db=-1.0)
+        else:
+            self.desc = L.FrontendDesc(kind=1, n_fft=mel.n_fft, win_length=mel.n_fft, hop=mel.hop, n_mels=n_mels,
+                                       remove_dc=0, preemph=0.0, power=mel.desc.power, use_log=2, log_floor=1e-10,
+                                       post=1, n_out=n_mfcc, db_mult=10.0, top_db=80.0)
 
 
 class AudioFeaturizer:
     """音频特征器 (drop-in for mvector.data_utils.featurizer.AudioFeaturizer).
 
-    :param feature_method: 'Fbank' | 'MelSpectrogram'  ('Spectrogram' / 'MFCC' / HF models: not lowered, raise)
+    :param feature_method: 'Fbank' | 'MelSpectrogram' | 'Spectrogram' | 'MFCC'  (HF models: not lowered, raise)
     :param method_args: forwarded as **kwargs exactly like the reference (unknown keys -> TypeError)
     """
 
@@ -162,8 +259,10 @@ class AudioFeaturizer:
             self.feat_fun = MelSpectrogram(**method_args)
         elif feature_method == 'Fbank':
             self.feat_fun = KaldiFbank(**method_args)
-        elif feature_method in ('Spectrogram', 'MFCC'):
-            raise NotImplementedError(f'{feature_method} is not lowered yet (SURVEY.md 8f)')
+        elif feature_method == 'Spectrogram':
+            self.feat_fun = Spectrogram(**method_args)
+        elif feature_method == 'MFCC':
+            self.feat_fun = MFCC(**method_args)
         else:
             raise Exception(f'预处理方法 {self._feature_method} 不存在!')
         self._engine = engine
@@ -179,9 +278,11 @@ class AudioFeaturizer:
         f = self.feat_fun
         start, count, off, w = f.bank
         win = np.ascontiguousarray(f.window, dtype=np.float32)
+        dct = getattr(f, 'dct', None)
         _check(self._engine.handle, L.lib().vp_frontend_set(
             self._engine.handle, C.byref(f.desc), win.ctypes.data_as(C.c_void_p), start.ctypes.data_as(C.c_void_p),
-            count.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p), int(w.size)))
+            count.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p), int(w.size),
+            dct.ctypes.data_as(C.c_void_p) if dct is not None else C.c_void_p()))
         self._configured = True
 
     @property
@@ -217,11 +318,11 @@ class AudioFeaturizer:
         keep = None
         if input_lens_ratio is not None:
             keep = self.keep_frames(input_lens_ratio, T).to(dev, non_blocking=True)
-        feats = torch.empty(B, T, f.n_mels, dtype=torch.float32, device=dev)
+        feats = torch.empty(B, T, self.feature_dim, dtype=torch.float32, device=dev)
         lib = L.lib()
         scratch = torch.empty(max(int(lib.vp_frontend_scratch_floats(self._engine.handle, B, Lp)), 1),
                               dtype=torch.float32, device=dev)
-        fn = lib.vp_fbank if f.desc.kind == 0 else lib.vp_melspec
+        fn = lib.vp_fbank if f.desc.kind == 0 else (lib.vp_mfcc if f.desc.post == 1 else lib.vp_melspec)
         _check(self._engine.handle, fn(self._engine.handle, C.c_void_p(w.data_ptr()), B, Lp,
                                        C.c_void_p(keep.data_ptr()) if keep is not None else C.c_void_p(),
                                        C.c_void_p(feats.data_ptr()), C.c_void_p(scratch.data_ptr()),
@@ -235,6 +336,10 @@ class AudioFeaturizer:
         """featurizer.py:93-111."""
         if self._feature_method == 'MelSpectrogram':
             return self._method_args.get('n_mels', 128)
+        elif self._feature_method == 'Spectrogram':
+            return self._method_args.get('n_fft', 400) // 2 + 1
+        elif self._feature_method == 'MFCC':
+            return self._method_args.get('n_mfcc', 40)
         elif self._feature_method == 'Fbank':
             return self._method_args.get('num_mel_bins', 23)
         raise Exception('没有{}预处理方法'.format(self._feature_method))

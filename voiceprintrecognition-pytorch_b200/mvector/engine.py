@@ -194,6 +194,22 @@ class PlanBuilder:
         self.in_floats = rows * cols
         return View(L.BUF_INPUT, cols, 0, cols)
 
+    def input_view1d(self, cols, rows, rows_per_utt):
+        """Input of a 1-D (channel = feature) model: CONV gathers float4 along channels, so a feature dim that is not a
+        multiple of 4 is first copied into a zero-padded workspace buffer (EW PAD_COPY)."""
+        v = self.input_view(cols, rows)
+        if cols % 4 == 0:
+            return v
+        cp = (cols + 3) // 4 * 4
+        dst = self.alloc(rows, cp)
+        o = self._new(L.OP_EW)
+        o.mode = L.EW_PAD_COPY
+        o.src, o.in_ld, o.in_coff, o.Cin = v.off, v.ld, v.coff, cols
+        o.dst, o.out_ld, o.out_coff, o.Cout = dst.off, dst.ld, dst.coff, cp
+        o.Tin, o.Fin = rows_per_utt, 1
+        self.ops.append(o)
+        return dst
+
     def output_view(self, cols, rows):
         self.out_floats = rows * cols
         return View(L.BUF_OUTPUT, cols, 0, cols)

@@ -25,8 +25,13 @@ def _tdnn_block_shapes(d, p, cin, cout, k):
 
 
 def conv1d_weight(w):
-    """[Cout, Cin, k] -> [Cout, k*Cin] with K index = tap*Cin + ci (the gather order of the CONV op)."""
+    """[Cout, Cin, k] -> [Cout, k*Cin4] with K index = tap*Cin4 + ci (the gather order of the CONV op).  Cin4 = Cin
+    rounded up to a multiple of 4 with zero columns: only a first layer fed by an odd feature dim (Spectrogram's
+    n_fft/2+1 bins) is ever padded; its input comes through PlanBuilder.input_view1d."""
     w = _np64(w)
+    cin = w.shape[1]
+    if cin % 4:
+        w = np.concatenate([w, np.zeros((w.shape[0], -cin % 4, w.shape[2]), dtype=w.dtype)], axis=1)
     return np.ascontiguousarray(w.transpose(0, 2, 1)).reshape(w.shape[0], -1)
 
 
@@ -124,9 +129,11 @@ class EcapaTdnn(Backbone):
         for i, k in enumerate(ks):
             if dl[i] * (k - 1) // 2 >= T:
                 raise ValueError(f'{T} frames is too short for reflect padding {dl[i] * (k - 1) // 2}')
-        x_in = pb.input_view(self.input_size, M)
+        x_in = pb.input_view1d(self.input_size, M, T)
         x0 = pb.alloc(M, ch[0])
         self._tdnn_block(pb, x_in, x0, o['stem'], T, ks[0], dl[0])
+        if x_in.off != L.BUF_INPUT:
+            pb.free(x_in)
         cat = pb.alloc(M, ch[-1])
         xin, coff = x0, 0
         sc = self.res2net_scale

@@ -60,7 +60,7 @@ class TDNN(Backbone):
 
     def _lower(self, pb, B, T):
         o, c = self._off, self.channels
-        x = pb.input_view(self.input_size, B * T)
+        x = pb.input_view1d(self.input_size, B * T, T)
         t = T
         for i, (k, dil) in enumerate(zip(_KS, _DIL), start=1):
             tout = t - dil * (k - 1)
@@ -70,7 +70,7 @@ class TDNN(Backbone):
             y = pb.alloc(B * tout, c)
             pb.conv(x, y, e['w'], k * x.C, t, tout, KT=k, dT=dil, bias=e['b'], act=L.ACT_RELU,
                     post=(e['s'], e['h']) if i < 5 else None)
-            if i > 1:
+            if x.off != L.BUF_INPUT:
                 pb.free(x)
             x, t = y, tout
         width = pool_width(self.pooling_type, c)

@@ -207,10 +207,12 @@ class MVectorPredictor:
         if masked:
             keep_all = fz.keep_frames(torch.tensor([w.shape[0] / lmax for w in waves], dtype=torch.float32), T).to(dev)
         eng = fz.engine
-        F = fz.feat_fun.n_mels
+        F = fz.feature_dim
         D = self.predictor.embd_dim
         emb = torch.empty(B, D, dtype=torch.float32, device=dev)
         cb = min(self.CHUNK, B)
+        if fz.feat_fun.desc.post == 1 and fz.feat_fun.desc.top_db >= 0:
+            cb = B          # MFCC's top_db clamp takes the maximum over the whole call (featurizer.py:76 on the full batch)
         feats = torch.empty(cb * T * F, dtype=torch.float32, device=dev)
         scratch = torch.empty(max(int(L.lib().vp_frontend_scratch_floats(eng.handle, cb, lmax)), 1), dtype=torch.float32,
                               device=dev)
