@@ -141,6 +141,9 @@ typedef struct vp_op {
    * floats with the 16-byte chunks of every 128-byte row XOR-swizzled by (row & 7) -- the UMMA SWIZZLE_128B K-major
    * shared-memory image, so one bulk-async copy lands a pipeline stage (see conv_tc.cu, mvector/engine.py::pack_tc) */
   int64_t w_tc;
+  /* optional accumulate-into view (or VP_BUF_NONE): after the epilogue, sum[m, sum_coff + n] += y[m, n].  Lets a Res2
+   * chain hand "x_{j+1} + y_j" to the next conv as ONE source (in place over x_{j+1}) instead of gathering two. */
+  int64_t sum;
   /* source geometry: rows = B*Tin*Fin, each row in_ld floats, channels [in_coff, in_coff+Cin) */
   int32_t Tin, Fin, Cin, in_ld, in_coff;
   int32_t src2_mode, src2_ld, src2_coff, Cin2;   /* ADD: same Cin; CONCAT: channels Cin..Cin+Cin2 come from src2 */
@@ -155,7 +158,8 @@ typedef struct vp_op {
   int32_t seg_len, n_seg;  /* gate / ubias / SEG_CONTEXT rows per utterance: row (b*n_seg + min(t/seg_len, n_seg-1)) */
   float   eps;
   int32_t tc_bn;           /* N tile of w_tc: 256 if Cout >= 256 else Cout rounded up to 16 */
-  int32_t reserved[6];
+  int32_t sum_ld, sum_coff;
+  int32_t reserved[4];
 } vp_op;
 
 /* Upload the packed fp32 weight arena (host pointer, copied to the device; replaces any previous arena). */

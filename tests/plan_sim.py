@@ -115,6 +115,8 @@ class Sim:
             v = v + self.rd(o.res, M, o.res_ld, o.res_coff, o.Cout)
         v = _act(v, o.act2)
         self.wr(o.dst, M, o.out_ld, o.out_coff, o.Cout, v)
+        if o.sum != L.BUF_NONE:
+            self.wr(o.sum, M, o.sum_ld, o.sum_coff, o.Cout, self.rd(o.sum, M, o.sum_ld, o.sum_coff, o.Cout) + v)
 
     def colstats(self, o):
         R = o.Tin * o.Fin

@@ -25,7 +25,8 @@ def _run_case(case, engine_id):
     c_x2 = Cin
     c_res = c_x2 + (Cin2 if src2_mode == L.SRC2_CONCAT else (Cin if src2_mode == L.SRC2_ADD else 0))
     c_gu = c_res + (N if case.get('res') else 0)
-    width = c_gu + (2 * N if (case.get('gate') or case.get('ubias')) else 0)
+    c_sum = c_gu + (2 * N if (case.get('gate') or case.get('ubias')) else 0)
+    width = c_sum + (N if case.get('sum') else 0)
     width = (width + 3) // 4 * 4
     rows = max(rows_in, rows_out, B * n_seg)
     X = (rng.standard_normal((rows, width)) * case.get('scale', 1.0)).astype(np.float32)
@@ -52,20 +53,28 @@ def _run_case(case, engine_id):
     if case.get('ubias'):
         ubias = pb.alloc(B * n_seg, N)
         pb.ew(L.EW_COPY, inp.cols(c_gu + N, N), ubias, 1).B = B * n_seg
-    out = pb.output_view(N, rows_out)
+    n_out = 2 * N if case.get('sum') else N
+    out_full = pb.output_view(n_out, rows_out)
+    out = out_full.cols(0, N)
+    acc = None
+    if case.get('sum'):                    # accumulate-into view: prefilled, then acc += conv output (Res2 chains)
+        acc = pb.alloc(rows_out, N)
+        pb.ew(L.EW_COPY, inp.cols(c_sum, N), acc, Tout * Fout)
     pb.conv(src, out, w, K, Tin, Tout, Fin=Fin, Fout=Fout, KT=KT, KF=KF, sT=case.get('sT', 1), sF=case.get('sF', 1),
             dT=case.get('dT', 1), dF=1, padT=case.get('padT', 0), padF=case.get('padF', 0),
             pad_mode=case.get('pad_mode', L.PAD_ZERO), bias=bias, pre=pre, pre_relu=bool(case.get('pre')), post=post,
             act=case.get('act', L.ACT_NONE), act2=case.get('act2', L.ACT_NONE), res=res, gate=gate, ubias=ubias,
-            seg_len=case.get('seg_len'), n_seg=n_seg, src2=src2, src2_mode=src2_mode)
+            seg_len=case.get('seg_len'), n_seg=n_seg, src2=src2, src2_mode=src2_mode, sum_into=acc)
+    if acc is not None:
+        pb.ew(L.EW_COPY, acc, out_full.cols(N, N), Tout * Fout)
     eng = Engine()
     blob = arena.blob()
     eng.load_weights(blob)
     prog = Program(eng, pb)
-    y = torch.empty(rows_out, N, device='cuda')
+    y = torch.empty(rows_out, n_out, device='cuda')
     prog.run(torch.from_numpy(X).cuda().contiguous(), y)
     torch.cuda.synchronize()
-    ref = Sim(pb, blob, X).run().reshape(rows_out, N)
+    ref = Sim(pb, blob, X).run().reshape(rows_out, n_out)
     got = y.cpu().numpy()
     eng.close()
     return got, ref
@@ -91,6 +100,10 @@ CASES = dict(
     n_tail_192=dict(seed=13, B=3, Tin=400, Tout=400, Cin=96, N=192, bias=True),
     long_k_chunked_9216=dict(seed=15, B=6, Tin=40, Fin=20, Tout=20, Fout=10, Cin=1024, N=256, KT=3, KF=3, sT=2, sF=2, padT=1, padF=1),
     long_k_chunked_4096_n128=dict(seed=16, B=7, Tin=151, Tout=151, Cin=4096, N=128, ubias=True, act=1, post=True, act2=4),
+    res2_k3_dil3_reflect_sum=dict(seed=17, B=9, Tin=298, Tout=298, Cin=64, N=64, KT=3, dT=3, padT=3, pad_mode=1, bias=True,
+                                  act=1, post=True, sum=True),
+    conv2d_3x3_sum_hardtanh=dict(seed=18, B=2, Tin=50, Fin=20, Tout=50, Fout=20, Cin=16, N=16, KT=3, KF=3, padT=1, padF=1,
+                                 bias=True, act=2, sum=True),
     k_tail_72=dict(seed=14, B=11, Tin=100, Tout=100, Cin=24, N=24, KT=3, padT=1, bias=True, act=2),
 )
 

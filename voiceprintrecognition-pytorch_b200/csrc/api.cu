@@ -313,6 +313,11 @@ static int validate_op(vp_program* p, const vp_op& o, int i) {
         TRY(check_act_buf(p, "src2", o.src2, view_floats(rows_in, o.src2_ld, o.src2_coff, o.src2_mode == VP_SRC2_CONCAT ? o.Cin2 : o.Cin), false, i));
       TRY(check_act_buf(p, "dst", o.dst, view_floats(rows_out, o.out_ld, o.out_coff, o.Cout), true, i));
       if (o.res != VP_BUF_NONE) TRY(check_act_buf(p, "res", o.res, view_floats(rows_out, o.res_ld, o.res_coff, o.Cout), false, i));
+      if (o.sum != VP_BUF_NONE) {
+        if (o.kind == VP_OP_CONV_C1 || o.sum < 0 || (o.sum_ld & 3) || (o.sum_coff & 3) || (o.Cout & 3))
+          return fail(h, VP_ERR_UNSUPPORTED, "op %d: sum view must be a 4-float aligned workspace view of a CONV op", i);
+        TRY(check_act_buf(p, "sum", o.sum, view_floats(rows_out, o.sum_ld, o.sum_coff, o.Cout), true, i));
+      }
       if (o.gate != VP_BUF_NONE) TRY(check_act_buf(p, "gate", o.gate, (size_t)o.B * o.n_seg * o.Cout, false, i));
       if (o.ubias != VP_BUF_NONE) TRY(check_act_buf(p, "ubias", o.ubias, (size_t)o.B * o.n_seg * o.Cout, false, i));
       if (o.w_tc >= 0) {
@@ -460,6 +465,7 @@ static void fill_conv(const vp_program* p, const vp_op& o, const float* feats, f
   c.src = rd(p, o.src, feats, emb);
   c.src2 = o.src2_mode == VP_SRC2_NONE ? nullptr : rd(p, o.src2, feats, emb);
   c.dst = const_cast<float*>(rd(p, o.dst, feats, emb));
+  c.sum = const_cast<float*>(rd(p, o.sum, feats, emb)); c.sum_ld = o.sum_ld; c.sum_coff = o.sum_coff;
   c.res = rd(p, o.res, feats, emb); c.gate = rd(p, o.gate, feats, emb); c.ubias = rd(p, o.ubias, feats, emb);
   c.w = wt(p, o.w); c.w_tc = wt(p, o.w_tc); c.tc_bn = o.tc_bn; c.bias = wt(p, o.bias); c.pre_s = wt(p, o.pre_s); c.pre_h = wt(p, o.pre_h);
   c.post_s = wt(p, o.post_s); c.post_h = wt(p, o.post_h);

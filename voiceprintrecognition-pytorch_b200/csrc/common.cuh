@@ -8,14 +8,14 @@ namespace vpb {
 
 // Resolved (device-pointer) form of a vp_op, passed to kernels by value.
 struct ConvParams {
-  const float* src; const float* src2; float* dst; const float* res; const float* gate; const float* ubias;
+  const float* src; const float* src2; float* dst; float* sum; const float* res; const float* gate; const float* ubias;
   const float* w; const float* w_tc; const float* bias; const float* pre_s; const float* pre_h; const float* post_s; const float* post_h;
   int M, N, K;                       // M = B*Tout*Fout rows, N = Cout, K = KT*KF*CinTot
   int B, Tin, Fin, Cin, CinTot, in_ld, in_coff;
   int src2_mode, src2_ld, src2_coff;
   int Tout, Fout, out_ld, out_coff, res_ld, res_coff;
   int KT, KF, sT, sF, dT, dF, padT, padF, pad_mode;
-  int w_ld, pre_relu, act, act2, seg_len, n_seg, tc_bn;
+  int w_ld, pre_relu, act, act2, seg_len, n_seg, tc_bn, sum_ld, sum_coff;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -109,6 +109,19 @@ __device__ __forceinline__ float epilogue1(const ConvParams& p, float acc, int m
   if (p.gate) v *= __ldg(p.gate + (size_t)urow * p.N + n);
   if (p.res) v += __ldg(p.res + (size_t)m * p.res_ld + p.res_coff + n);
   return apply_act(v, p.act2);
+}
+
+// Optional accumulate-into view: sum[m, n] += y (each element is owned by exactly one thread of one launch).
+__device__ __forceinline__ void sum_add1(const ConvParams& p, int m, int n, float y) {
+  if (p.sum) p.sum[(size_t)m * p.sum_ld + p.sum_coff + n] += y;
+}
+__device__ __forceinline__ void sum_add4(const ConvParams& p, int m, int n, float4 y) {
+  if (p.sum) {
+    float4* q = reinterpret_cast<float4*>(p.sum + (size_t)m * p.sum_ld + p.sum_coff + n);
+    float4 s = *q;
+    s.x += y.x; s.y += y.y; s.z += y.z; s.w += y.w;
+    *q = s;
+  }
 }
 
 __device__ __forceinline__ int urow_of(const ConvParams& p, int m) {

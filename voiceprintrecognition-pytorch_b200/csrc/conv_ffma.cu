@@ -125,17 +125,26 @@ __global__ void __launch_bounds__(256, 2) conv_ffma_kernel(const __grid_constant
           o.z = epilogue1(p, acc[i][h * 4 + 2], m, n + 2, urow);
           o.w = epilogue1(p, acc[i][h * 4 + 3], m, n + 3, urow);
           *reinterpret_cast<float4*>(orow + n) = o;
+          sum_add4(p, m, n, o);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (n + j < p.N) orow[n + j] = epilogue1(p, acc[i][h * 4 + j], m, n + j, urow);
+            if (n + j < p.N) {
+              const float y = epilogue1(p, acc[i][h * 4 + j], m, n + j, urow);
+              orow[n + j] = y;
+              sum_add1(p, m, n + j, y);
+            }
         }
       }
     } else {
       const int n = n0 + tx * TN;
 #pragma unroll
       for (int j = 0; j < TN; ++j)
-        if (n + j < p.N) orow[n + j] = epilogue1(p, acc[i][j], m, n + j, urow);
+        if (n + j < p.N) {
+          const float y = epilogue1(p, acc[i][j], m, n + j, urow);
+          orow[n + j] = y;
+          sum_add1(p, m, n + j, y);
+        }
     }
   }
 }
@@ -188,7 +197,11 @@ __global__ void __launch_bounds__(256) linear_small_m_kernel(const __grid_consta
     if (lane == j) mine = t;
   }
   const int n = n0 + lane;
-  if (mok && n < p.N) p.dst[(size_t)m * p.out_ld + p.out_coff + n] = epilogue1(p, mine, m, n, urow_of(p, m));
+  if (mok && n < p.N) {
+    const float y = epilogue1(p, mine, m, n, urow_of(p, m));
+    p.dst[(size_t)m * p.out_ld + p.out_coff + n] = y;
+    sum_add1(p, m, n, y);
+  }
 }
 
 static bool small_m_ok(const ConvParams& p) {

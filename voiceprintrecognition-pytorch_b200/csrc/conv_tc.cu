@@ -205,42 +205,45 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const int chunk = t & 7;
     const int r0 = t >> 3;                 // 0..31
     const bool pointwise = (p.KT * p.KF == 1);
-    uint32_t it = 0;
     // The (tile, K block) pairs of this CTA form ONE flat stream: the gather cursor runs DEPTH items ahead of the publish
     // cursor and crosses tile boundaries, so the load pipeline never drains between tiles.
     const int my_tiles = (total_groups - cluster_id + n_clusters - 1) / n_clusters;
     const int total_items = my_tiles * a.k_blocks;
     RowInfo rows[ROWS_PER_THREAD];
-    int rows_tile = -1;
+    // Gather cursor.  gather() is always called for consecutive items q = 0, 1, 2, ..., so the (tile, K block, tap,
+    // channel) decomposition of q is kept incrementally -- no integer division per K block (ncu, Res2 convs: the old
+    // per-call divisions + 64-bit row arithmetic made the producers instruction-issue bound at N = 64).
+    int g_tl = 0, g_kb = 0;                    // tile (local index) and K block of the next item to gather
+    int g_k = chunk * 4;                       // this thread's first k of that K block
+    int g_ci = 0, g_kt = 0, g_kf = 0;          // channel / tap position of g_k
+    auto cursor_reset = [&]() {
+      g_kb = 0; g_k = chunk * 4; g_ci = g_k; g_kt = 0; g_kf = 0;
+      if (!pointwise)
+        while (g_ci >= p.CinTot) { g_ci -= p.CinTot; if (++g_kf == p.KF) { g_kf = 0; ++g_kt; } }
+    };
+    cursor_reset();
     {
       // Register prefetch slots.  gather() ONLY issues loads (no instruction may read a loaded register before publish():
       // even a predicated-off consumer stalls on the load's scoreboard and would serialise the loads); add / BN-ReLU
       // prologue are applied in publish().  MODE 0: plain or channel-concat source, 3 K blocks in flight; MODE 1: second
       // source added (x_i + y_{i-1}); MODE 2: per-channel affine(+ReLU) prologue; 2 K blocks in flight for 1 and 2.
       Slot<MODE> sl0, sl1, sl2;
-      auto gather = [&](int q, Slot<MODE>& sl) {
-        const int tl = q / a.k_blocks;
-        const int kb = q - tl * a.k_blocks;
-        if (tl != rows_tile) {                 // gather cursor entered a new tile: decode its 4 rows
-          rows_tile = tl;
-          const int g = cluster_id + tl * n_clusters;
+      auto gather = [&](Slot<MODE>& sl) {
+        if (g_kb == 0) {                       // cursor entered a new tile: decode its 4 rows
+          const int g = cluster_id + g_tl * n_clusters;
           const int m0 = ((g / a.n_tiles) * (int)C + (int)crank) * BM;
 #pragma unroll
-          for (int i = 0; i < ROWS_PER_THREAD; ++i) rows[i] = decode_row(p, m0 + r0 + 32 * i);
+          for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+            rows[i] = decode_row(p, m0 + r0 + 32 * i);
+            if (!rows[i].valid) rows[i].t0 = -(1 << 28);        // fails every bounds test below (also after reflection)
+          }
         }
-        const int k = kb * BK + chunk * 4;
-        int ci = k, dt = 0, df = 0;
-        if (!pointwise) {
-          const int tap = k / p.CinTot;
-          ci = k - tap * p.CinTot;
-          const int kt = tap / p.KF;
-          dt = kt * p.dT;
-          df = (tap - kt * p.KF) * p.dF;
-        }
-        const bool kok = k < p.K && !(a.debug & 2);
+        const int ci = g_ci;
+        const int dt = g_kt * p.dT, df = g_kf * p.dF;
+        const bool kok = g_k < p.K && !(a.debug & 2);
         const bool second = (MODE == 0) && (p.src2_mode == VP_SRC2_CONCAT) && (ci >= p.Cin);
-        const float* base = second ? p.src2 + p.src2_coff + (ci - p.Cin) : p.src + p.in_coff + ci;
-        const int ld = second ? p.src2_ld : p.in_ld;
+        const char* base = reinterpret_cast<const char*>(second ? p.src2 + p.src2_coff + (ci - p.Cin) : p.src + p.in_coff + ci);
+        const uint32_t ldb = (uint32_t)(second ? p.src2_ld : p.in_ld) * 4u;      // row pitch in bytes
         if constexpr (MODE == 2) {
           sl.ps = make_float4(1.f, 1.f, 1.f, 1.f);
           sl.ph = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -258,22 +261,36 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             if (ti < 0) ti = -ti;
             if (ti >= p.Tin) ti = 2 * (p.Tin - 1) - ti;
           }
-          const bool ok = kok && rows[i].valid && ti >= 0 && ti < p.Tin && fi >= 0 && fi < p.Fin;
-          const size_t row = ok ? (size_t)rows[i].base + (size_t)ti * p.Fin + fi : 0;
+          const bool ok = kok && (unsigned)ti < (unsigned)p.Tin && (unsigned)fi < (unsigned)p.Fin;
+          const uint32_t r = (uint32_t)(rows[i].base + ti * p.Fin + fi);       // source row index (< 2^31 rows)
           sl.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok) sl.v[i] = __ldg(reinterpret_cast<const float4*>(base + row * ld));
+          if (ok) sl.v[i] = __ldg(reinterpret_cast<const float4*>(base + (uint64_t)r * ldb));
           if constexpr (MODE == 1) {
             sl.u[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok) sl.u[i] = __ldg(reinterpret_cast<const float4*>(p.src2 + row * p.src2_ld + p.src2_coff + ci));
+            if (ok)
+              sl.u[i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(p.src2 + p.src2_coff + ci) +
+                                                              (uint64_t)r * ((uint32_t)p.src2_ld * 4u)));
           }
           if constexpr (MODE == 2) sl.okmask |= ok ? (1u << i) : 0u;
         }
+        // advance the cursor by one K block
+        if (++g_kb == a.k_blocks) {
+          ++g_tl;
+          cursor_reset();
+        } else {
+          g_k += BK;
+          g_ci += BK;
+          if (!pointwise)
+            while (g_ci >= p.CinTot) { g_ci -= p.CinTot; if (++g_kf == p.KF) { g_kf = 0; ++g_kt; } }
+        }
       };
       constexpr int DEPTH = (MODE == 0) ? 3 : 2;
+      int p_s = 0;
+      uint32_t p_ph = 0;
       auto publish = [&](int q, Slot<MODE>& sl) {
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1;
-        ++it;
+        const int s = p_s;
+        const uint32_t ph = p_ph;
+        if (++p_s == S) { p_s = 0; p_ph ^= 1u; }
         mbar_wait(empty0 + 8 * s, ph ^ 1);
         const uint32_t a_hi = smem_base + s * stage_bytes;
         const uint32_t a_lo = a_hi + A_TILE;
@@ -299,12 +316,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(full0 + 8 * s);     // one arrival per producer warp
-        if (q + DEPTH < total_items) gather(q + DEPTH, sl);   // refill this slot: DEPTH K blocks of loads stay in flight
+        if (q + DEPTH < total_items) gather(sl);   // refill this slot (item q + DEPTH): DEPTH K blocks of loads stay in flight
       };
-      if (total_items > 0) gather(0, sl0);
-      if (total_items > 1) gather(1, sl1);
+      if (total_items > 0) gather(sl0);
+      if (total_items > 1) gather(sl1);
       if constexpr (DEPTH == 3) {
-        if (total_items > 2) gather(2, sl2);
+        if (total_items > 2) gather(sl2);
         for (int q = 0; q < total_items; q += 3) {
           publish(q, sl0);
           if (q + 1 < total_items) publish(q + 1, sl1);
@@ -320,20 +337,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   } else if (warp == 4 + PRODUCER_WARPS) {
     // =========================== B loader (bulk async copy) ===========================
     if (lane == 0) {
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;                                        // stage / phase cursors, advanced without divisions
       const uint32_t slice = 2u * b_tile / C;                 // this CTA's share of every B stage
       for (int g = cluster_id; g < total_groups; g += n_clusters) {
         const int nt = g % a.n_tiles;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(a.w_tc) + (size_t)nt * a.k_blocks * (2u * b_tile) + crank * slice;
-        for (int kb = 0; kb < a.k_blocks; ++kb, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1;
+        for (int kb = 0; kb < a.k_blocks; ++kb) {
           mbar_wait(empty0 + 8 * s, ph ^ 1);
-          if (a.debug & 1) { mbar_arrive(full0 + 8 * s); continue; }
-          mbar_expect_tx(full0 + 8 * s, 2u * b_tile);          // the whole stage lands here (own slice + peers' multicasts)
-          const uint32_t dst = smem_base + s * stage_bytes + 2u * A_TILE + crank * slice;
-          if (C > 1) bulk_copy_g2s_mcast(dst, src + (size_t)kb * (2u * b_tile), slice, full0 + 8 * s, cmask);
-          else bulk_copy_g2s(dst, src + (size_t)kb * (2u * b_tile), slice, full0 + 8 * s);
+          if (a.debug & 1) {
+            mbar_arrive(full0 + 8 * s);
+          } else {
+            mbar_expect_tx(full0 + 8 * s, 2u * b_tile);        // the whole stage lands here (own slice + peers' multicasts)
+            const uint32_t dst = smem_base + s * stage_bytes + 2u * A_TILE + crank * slice;
+            if (C > 1) bulk_copy_g2s_mcast(dst, src + (size_t)kb * (2u * b_tile), slice, full0 + 8 * s, cmask);
+            else bulk_copy_g2s(dst, src + (size_t)kb * (2u * b_tile), slice, full0 + 8 * s);
+          }
+          if (++s == S) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -342,7 +362,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     if (lane == 0) {
       // kind::tf32 instruction descriptor: D=F32 (bit 4), A=B=TF32 (2 at bits 7 and 10), K-major, N>>3 @17, M>>4 @24
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      uint32_t it = 0, ccount = 0;
+      uint32_t ccount = 0;
+      int s = 0;
+      uint32_t sph = 0;                                       // stage / phase cursors, advanced without divisions
       for (int g = cluster_id; g < total_groups; g += n_clusters) {
         // Long-K layers are accumulated in chunks of `kc` K blocks, each into a fresh TMEM accumulator; the epilogue
         // warps fold the chunks into a running fp32 sum with correctly rounded adds.  (The tensor core truncates on every
@@ -354,9 +376,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           const uint32_t d = tmem_base + (uint32_t)(acc * BN);
           const int kb0 = ch * a.kc;
           const int kb1 = (kb0 + a.kc < a.k_blocks) ? kb0 + a.kc : a.k_blocks;
-          for (int kb = kb0; kb < kb1; ++kb, ++it) {
-            const int s = it % S;
-            mbar_wait(full0 + 8 * s, (it / S) & 1);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(full0 + 8 * s, sph);
             tc_fence_after();
             const uint32_t a_hi = smem_base + s * stage_bytes, a_lo = a_hi + A_TILE;
             const uint32_t b_hi = a_hi + 2u * A_TILE, b_lo = b_hi + b_tile;
@@ -371,6 +392,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             }
             if (C > 1) umma_commit_mcast(empty0 + 8 * s, cmask);   // frees the stage in every CTA of the cluster
             else umma_commit(empty0 + 8 * s);                 // frees the smem stage when these MMAs retire
+            if (++s == S) { s = 0; sph ^= 1u; }
           }
           umma_commit(tfull0 + 8 * acc);                      // chunk accumulator ready for the epilogue warps
         }
@@ -517,6 +539,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             if (rowok & (1u << i)) *reinterpret_cast<float4*>(optr[i] + c0) = v[i];
+          if (p.sum) {                         // accumulate-into view (Res2 chains): sum[m, n] += y[m, n]
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (rowok & (1u << i)) sum_add4(p, mbase + rsub + 4 * i, n, v[i]);
+          }
         }
         __syncwarp();
       }

@@ -29,14 +29,15 @@ class FrontendDesc(C.Structure):
 class Op(C.Structure):
     _fields_ = ([('kind', C.c_int32), ('mode', C.c_int32), ('engine', C.c_int32), ('B', C.c_int32)]
                 + [(n, C.c_int64) for n in ('src', 'src2', 'dst', 'res', 'gate', 'ubias',
-                                            'w', 'bias', 'pre_s', 'pre_h', 'post_s', 'post_h', 'w_tc')]
+                                            'w', 'bias', 'pre_s', 'pre_h', 'post_s', 'post_h', 'w_tc', 'sum')]
                 + [(n, C.c_int32) for n in ('Tin', 'Fin', 'Cin', 'in_ld', 'in_coff',
                                             'src2_mode', 'src2_ld', 'src2_coff', 'Cin2',
                                             'Tout', 'Fout', 'Cout', 'out_ld', 'out_coff',
                                             'res_ld', 'res_coff',
                                             'KT', 'KF', 'sT', 'sF', 'dT', 'dF', 'padT', 'padF', 'pad_mode',
                                             'w_ld', 'pre_relu', 'act', 'act2', 'seg_len', 'n_seg')]
-                + [('eps', C.c_float), ('tc_bn', C.c_int32), ('reserved', C.c_int32 * 6)])
+                + [('eps', C.c_float), ('tc_bn', C.c_int32), ('sum_ld', C.c_int32), ('sum_coff', C.c_int32),
+                   ('reserved', C.c_int32 * 4)])
 
 
 class VpError(RuntimeError):

@@ -222,7 +222,7 @@ class PlanBuilder:
         o = L.Op()
         o.kind = kind
         o.B = self.B
-        for f in ('src', 'src2', 'dst', 'res', 'gate', 'ubias', 'w', 'bias', 'pre_s', 'pre_h', 'post_s', 'post_h', 'w_tc'):
+        for f in ('src', 'src2', 'dst', 'res', 'gate', 'ubias', 'w', 'bias', 'pre_s', 'pre_h', 'post_s', 'post_h', 'w_tc', 'sum'):
             setattr(o, f, -1)
         o.Fin = o.Fout = 1
         o.KT = o.KF = o.sT = o.sF = o.dT = o.dF = 1
@@ -232,7 +232,7 @@ class PlanBuilder:
     def conv(self, src, dst, w, w_ld, Tin, Tout, Fin=1, Fout=1, KT=1, KF=1, sT=1, sF=1, dT=1, dF=1, padT=0, padF=0,
              pad_mode=L.PAD_ZERO, bias=-1, pre=None, pre_relu=False, post=None, act=L.ACT_NONE, act2=L.ACT_NONE,
              res=None, gate=None, ubias=None, seg_len=None, n_seg=1, src2=None, src2_mode=L.SRC2_NONE,
-             engine=None, B=None, c1=False):
+             engine=None, B=None, c1=False, sum_into=None):
         o = self._new(L.OP_CONV_C1 if c1 else L.OP_CONV)
         if B is not None:
             o.B = B
@@ -267,6 +267,9 @@ class PlanBuilder:
                 o.Cin2 = src2.C
             else:
                 assert src2.C == src.C
+        if sum_into is not None:           # sum_into[m, :] += y[m, :] after the epilogue (Res2 chains: x_{j+1} += y_j in place)
+            assert sum_into.C == dst.C and not c1
+            o.sum, o.sum_ld, o.sum_coff = sum_into.off, sum_into.ld, sum_into.coff
         self._check_conv(o)
         self.ops.append(o)
         return o

@@ -145,6 +145,10 @@ class EcapaTdnn(Backbone):
             self._tdnn_block(pb, xin, t1, blk['tdnn1'], T)
             y = pb.alloc(M, c)
             pb.ew(L.EW_COPY, t1.cols(0, w), y.cols(0, w), T)
+            # Res2Net chain (ecapa_tdnn.py Res2NetBlock.forward): y_j = block_j(x_j + y_{j-1}); the add rides in the gather of
+            # conv j (second source).  Measured alternative (round 1, B200): letting conv j-1's epilogue add its output
+            # into x_j in place (PlanBuilder.conv(sum_into=...)) so that conv j gathers ONE source was SLOWER here
+            # (64x192 convs 42 -> 80 us: the read-modify-write lands on the epilogue warps' critical path), so it is not used.
             for j in range(1, sc):
                 self._tdnn_block(pb, t1.cols(j * w, w), y.cols(j * w, w), blk['res2'][j - 1], T, ks[i], dl[i],
                                  src2=y.cols((j - 1) * w, w) if j >= 2 else None)
