@@ -540,9 +540,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           for (int i = 0; i < 8; ++i)
             if (rowok & (1u << i)) *reinterpret_cast<float4*>(optr[i] + c0) = v[i];
           if (p.sum) {                         // accumulate-into view (Res2 chains): sum[m, n] += y[m, n]
+            // all eight loads first, then the adds and stores: written as load-add-store per row the possible aliasing
+            // between rows forces the compiler to serialise eight global round trips per chunk
+            float4 sv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              sv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (rowok & (1u << i))
+                sv[i] = *reinterpret_cast<const float4*>(p.sum + (size_t)(mbase + rsub + 4 * i) * p.sum_ld + p.sum_coff + n);
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              if (rowok & (1u << i)) sum_add4(p, mbase + rsub + 4 * i, n, v[i]);
+              if (rowok & (1u << i)) {
+                sv[i].x += v[i].x; sv[i].y += v[i].y; sv[i].z += v[i].z; sv[i].w += v[i].w;
+                *reinterpret_cast<float4*>(p.sum + (size_t)(mbase + rsub + 4 * i) * p.sum_ld + p.sum_coff + n) = sv[i];
+              }
           }
         }
         __syncwarp();
