@@ -296,6 +296,45 @@ def main():
                         min_dcf_05=np.float64(compute_dcf(fnr, fpr, p_target=0.05, c_miss=10, c_fa=1)))
     manifest['metrics'] = dict(n=4000, note='mvector.metric.metrics on seeded random scores (rounded: ties present)')
 
+    # ---- diarization glue (infer_utils/speaker_diarization.py): chunking, spectral clustering, post-processing ----
+    from mvector.infer_utils.speaker_diarization import SpeakerDiarization as RefSD
+    dr = np.random.RandomState(3)
+    sd_ref = RefSD()
+    sr = 16000
+    vad_segments = []
+    t0 = 0.0
+    for dur in (4.1, 0.9, 6.35, 2.0, 3.77):                       # seconds of "speech", 0.4 s gaps
+        n = int((t0 + dur) * sr) - int(t0 * sr)
+        vad_segments.append([round(t0, 3), round(t0 + dur, 3), dr.randn(n).astype(np.float32)])
+        t0 = round(t0 + dur + 0.4, 3)
+    for seg in vad_segments:                                       # the reference's own consistency rule
+        seg[2] = seg[2][:int(seg[1] * sr) - int(seg[0] * sr)]
+        if seg[2].shape[0] < int(seg[1] * sr) - int(seg[0] * sr):
+            seg[2] = np.pad(seg[2], (0, int(seg[1] * sr) - int(seg[0] * sr) - seg[2].shape[0]))
+    sd_ref._check_audio_list(vad_segments)
+    chunks = sd_ref._chunk(vad_segments)
+    # embeddings: 3 speakers taking turns over the chunks (+ noise), two of them close enough to test the cosine merge
+    centres = dr.randn(3, 32).astype(np.float32)
+    centres[2] = centres[1] + 0.35 * dr.randn(32).astype(np.float32)
+    turn = np.array([(i // 5) % 3 for i in range(len(chunks))])
+    emb = (centres[turn] + 0.15 * dr.randn(len(chunks), 32)).astype(np.float32)
+    dz = {'n_vad': np.int32(len(vad_segments)), 'chunk_times': np.array([[c[0], c[1]] for c in chunks]),
+          'chunk_sums': np.array([float(np.abs(c[2]).sum()) for c in chunks]), 'emb': emb}
+    for i, seg in enumerate(vad_segments):
+        dz[f'vad{i}_t'] = np.array([seg[0], seg[1]])
+        dz[f'vad{i}_x'] = seg[2]
+    for tag, k in (('auto', None), ('k2', 2), ('k3', 3)):
+        np.random.seed(0)
+        labels, cen = sd_ref.clustering(emb.copy(), speaker_num=k)
+        out = sd_ref.postprocess([list(c) for c in chunks], labels)
+        dz[f'labels_{tag}'] = np.asarray(labels, dtype=np.int64)
+        dz[f'centres_{tag}'] = np.asarray(cen, dtype=np.float32)
+        dz[f'out_{tag}'] = np.array([[o['speaker'], o['start'], o['end']] for o in out], dtype=np.float64)
+        print('diarization', tag, labels.max() + 1, len(out))
+    np.savez_compressed(os.path.join(HERE, 'diarization.npz'), **dz)
+    manifest['diarization'] = dict(note='reference SpeakerDiarization._chunk / clustering / postprocess on seeded synthetic '
+                                        'VAD segments and 32-d chunk embeddings (np.random.seed(0) before every k_means)')
+
     # ---- default-config parameter-name/shape digests, for checking oracle.param_shapes on the GPU box ----
     defaults = {
         'EcapaTdnn': (80, dict(embd_dim=192, pooling_type='ASP', channels=[512, 512, 512, 512, 1536])),

@@ -509,3 +509,39 @@ def test_evaluate_matches_reference_golden(tmp_path, manifest):
     assert np.abs(captured['scores'] - z['scores']).max() < 2e-5          # cosine scores, embeddings within 1e-4 rel-L2
     assert abs(eer - float(z['eer'])) < 1e-6 and abs(min_dcf - float(z['min_dcf'])) < 1e-6
     assert abs(thr - float(z['threshold'])) < 2e-5
+
+
+def test_speaker_diarization_flow(manifest):
+    """MVectorPredictor.speaker_diarization (predict.py:365-395) = VAD segments -> 1.5 s chunks ->
+    predict_batch on the device -> spectral clustering -> post-processing.  The chunk embeddings are checked against the
+    oracle; the host glue is pinned on the reference's own classes by tests/test_host_logic.py."""
+    from mvector.predict import MVectorPredictor
+    from oracle import frontend as ofe, models as om
+    m = manifest['ecapa_small']
+    _, sd = load_golden('ecapa_small')
+    with tempfile.TemporaryDirectory() as td:
+        torch.save({'0.' + k: v for k, v in sd.items()}, os.path.join(td, 'model.pth'))
+        pred = MVectorPredictor(configs=_cfg(m['model'], m['model_args'], m['preprocess']), model_path=td, use_gpu=True)
+    rng = np.random.RandomState(4)
+    t = np.arange(16000 * 4) / 16000.0
+
+    def voice(f0, seed):                   # a "speaker" = harmonic stack + a little noise
+        x = sum(np.sin(2 * np.pi * f0 * h * t) / h for h in range(1, 9))
+        return (0.1 * x + 0.01 * np.random.RandomState(seed).randn(t.size)).astype(np.float32)
+
+    gap = np.zeros(8000, dtype=np.float32)
+    x = np.concatenate([gap, voice(110.0, 1), gap, voice(290.0, 2), gap, voice(110.0, 3), gap])
+    out = pred.speaker_diarization(x, sample_rate=16000, speaker_num=2)
+    assert isinstance(out, list) and len(out) >= 2
+    assert all(set(o) == {'speaker', 'start', 'end'} and o['end'] > o['start'] for o in out)
+    assert all(a['end'] <= b['start'] + 1e-6 for a, b in zip(out[:-1], out[1:]))
+    assert {o['speaker'] for o in out} <= {0, 1} and 0.0 <= out[0]['start'] and out[-1]['end'] <= x.size / 16000.0 + 1e-6
+    # the device embeddings of the chunks equal the oracle's on the same padded batch
+    from mvector.audio import AudioSegment
+    segs = pred.speaker_diarize.segments_audio(AudioSegment(x, 16000))
+    chunks = [s[2] for s in segs]
+    emb = pred.predict_batch(chunks)
+    xb, ratio = ofe.pad_batch(chunks)
+    feats = ofe.featurize(xb, ratio, m['preprocess']['feature_method'], m['preprocess']['method_args'])
+    ref = om.forward(m['model'], sd, feats, **m['model_args']).numpy()
+    assert rel_l2(emb, ref).max() < EMB_TOL

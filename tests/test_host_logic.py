@@ -269,3 +269,50 @@ def test_evaluate_host_logic_with_oracle_backend(tmp_path, manifest):
     assert np.array_equal(captured['labels'], z['labels'])
     assert np.abs(captured['scores'] - z['scores']).max() < 2e-6
     assert abs(eer - float(z['eer'])) < 1e-9 and abs(min_dcf - float(z['min_dcf'])) < 1e-9
+
+
+def test_diarization_glue_matches_reference_golden():
+    """infer_utils.speaker_diarization (chunking, spectral clustering, cosine merge, post-processing)
+    against outputs of the reference's own classes on seeded inputs (tests/golden/diarization.npz)."""
+    from mvector.infer_utils.speaker_diarization import SpeakerDiarization, SpectralCluster
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'diarization.npz'))
+    sd = SpeakerDiarization()
+    vad = [[float(z[f'vad{i}_t'][0]), float(z[f'vad{i}_t'][1]), z[f'vad{i}_x']] for i in range(int(z['n_vad']))]
+    sd._check_audio_list(vad)
+    chunks = sd._chunk(vad)
+    assert np.array_equal(np.array([[c[0], c[1]] for c in chunks]), z['chunk_times'])
+    assert np.allclose([float(np.abs(c[2]).sum()) for c in chunks], z['chunk_sums'], rtol=0, atol=0)
+    assert all(c[2].shape[0] == 24000 for c in chunks)
+    for tag, k in (('auto', None), ('k2', 2), ('k3', 3)):
+        np.random.seed(0)
+        labels, centres = sd.clustering(z['emb'].copy(), speaker_num=k)
+        assert np.array_equal(labels, z[f'labels_{tag}']), tag
+        assert np.allclose(centres, z[f'centres_{tag}'], atol=1e-6)
+        out = sd.postprocess([list(c) for c in chunks], labels)
+        got = np.array([[o['speaker'], o['start'], o['end']] for o in out], dtype=np.float64)
+        assert np.array_equal(got, z[f'out_{tag}']), tag
+    # pieces
+    sc = SpectralCluster()
+    A = sc.get_sim_mat(z['emb'])
+    assert np.allclose(np.diag(A), 1, atol=1e-6) and np.allclose(A, A.T, atol=1e-6)
+    P = sc.p_pruning(A.copy())
+    assert ((P != 0).sum(axis=1) == A.shape[0] - int((1 - 6.0 / A.shape[0]) * A.shape[0])).all()
+    assert SpeakerDiarization._correct_labels(np.array([2, 2, 0, 1, 0])).tolist() == [0, 0, 1, 2, 1]
+
+
+def test_energy_vad_and_diarization_segments():
+    from mvector.audio import AudioSegment
+    from mvector.infer_utils.speaker_diarization import SpeakerDiarization
+    rng = np.random.RandomState(0)
+    x = np.concatenate([np.zeros(8000), 0.2 * rng.randn(48000), np.zeros(16000), 0.1 * rng.randn(64000),
+                        np.zeros(4000)]).astype(np.float32)
+    seg = AudioSegment(x, 16000)
+    v = seg.vad(return_seconds=True)
+    assert len(v) == 2 and abs(v[0]['start'] - 0.5) < 0.05 and abs(v[0]['end'] - 3.5) < 0.05
+    assert abs(v[1]['start'] - 4.5) < 0.05 and abs(v[1]['end'] - 8.5) < 0.05
+    vs = seg.vad()
+    assert vs[0]['start'] == int(round(v[0]['start'] * 16000))
+    chunks = SpeakerDiarization().segments_audio(seg)
+    assert all(c[2].shape[0] == 24000 for c in chunks) and len(chunks) >= 6
+    with pytest.raises(AssertionError):                       # < 5 s of speech: the reference refuses too
+        SpeakerDiarization().segments_audio(AudioSegment(x[:40000], 16000))

@@ -1,6 +1,6 @@
 """Minimal AudioSegment: the surface of ``yeaudio.audio.AudioSegment`` that predict.py touches (predict.py:192-211):
 ``samples`` (float32 mono in [-1, 1]), ``sample_rate``, ``duration``, ``from_file`` / ``from_ndarray`` / ``from_bytes``,
-``resample``, ``normalize``.  yeaudio (requirements.txt:12) is a third-party package absent from the reference tree and
+``resample``, ``normalize``, ``vad``.  yeaudio (requirements.txt:12) is a third-party package absent from the reference tree and
 from this image; decoding/resampling sit OUTSIDE the parity boundary (parity starts at identical
 waveforms).  Decoding covers PCM WAV via the standard library only."""
 import io
@@ -72,3 +72,38 @@ class AudioSegment:
         if gain > max_gain_db:
             raise ValueError(f'cannot normalise to {target_db} dB: gain {gain} dB exceeds {max_gain_db} dB')
         self.samples = (self.samples * (10.0 ** (gain / 20.0))).astype(np.float32)
+
+    def vad(self, return_seconds=False, frame_ms=30.0, rel_threshold_db=-35.0, min_speech_ms=250.0, min_silence_ms=300.0):
+        """Voice-activity segments ``[{'start': ..., 'end': ...}, ...]`` in samples (or seconds).
+
+        Stand-in for yeaudio's model-based ``AudioSegment.vad`` (absent third-party code, outside the parity boundary):
+        frame RMS energy against a threshold ``rel_threshold_db`` below the loudest frame, silences shorter than
+        ``min_silence_ms`` bridged, bursts shorter than ``min_speech_ms`` dropped.  Same return format, so
+        ``SpeakerDiarization.segments_audio`` (infer_utils/speaker_diarization.py) consumes either."""
+        sr = self.sample_rate
+        hop = max(1, int(sr * frame_ms / 1000.0))
+        n = self.samples.shape[0]
+        if n < hop:
+            return []
+        nf = n // hop
+        x = self.samples[:nf * hop].astype(np.float64).reshape(nf, hop)
+        db = 10.0 * np.log10(np.maximum((x * x).mean(axis=1), 1e-12))
+        active = db > (db.max() + rel_threshold_db)
+        # runs of active frames
+        edges = np.flatnonzero(np.diff(np.concatenate([[0], active.astype(np.int8), [0]])))
+        runs = [[int(a), int(b)] for a, b in zip(edges[0::2], edges[1::2])]
+        merged = []
+        gap = int(round(min_silence_ms / frame_ms))
+        for r in runs:
+            if merged and r[0] - merged[-1][1] < gap:
+                merged[-1][1] = r[1]
+            else:
+                merged.append(r)
+        keep = int(round(min_speech_ms / frame_ms))
+        out = []
+        for a, b in merged:
+            if b - a < keep:
+                continue
+            st, ed = a * hop, min(b * hop, n)
+            out.append({'start': st / sr, 'end': ed / sr} if return_seconds else {'start': st, 'end': ed})
+        return out

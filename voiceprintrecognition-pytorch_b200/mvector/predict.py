@@ -8,8 +8,9 @@ Differences that are deliberate:
     the reference's ``batch_size`` argument (predict.py:261) is accepted and ignored -- chunking does not change
     results because every op is per-utterance, and padding/CMN/mask are computed on the full batch exactly like
     predict.py:244-258.
-  * ``speaker_diarization`` (predict.py:365-395: VAD + spectral clustering on CPU) is outside the hot path and raises
-    NotImplementedError.
+  * ``speaker_diarization`` (predict.py:365-395): chunk embeddings come from ``predict_batch`` on the device; chunking,
+    spectral clustering and post-processing are host glue (infer_utils/speaker_diarization.py); the VAD is an energy
+    detector standing in for yeaudio's model-based one (absent third-party code, outside the parity boundary).
 """
 import os
 import pickle
@@ -24,6 +25,7 @@ from loguru import logger
 from .audio import AudioSegment
 from .data_utils.featurizer import AudioFeaturizer
 from .engine import Engine
+from .infer_utils.speaker_diarization import SpeakerDiarization
 from .models import build_model
 from .utils.checkpoint import load_pretrained
 from .utils.utils import dict_to_object, print_arguments
@@ -59,6 +61,8 @@ class MVectorPredictor:
         self._pinned = None
         self._copy_stream = None
         self._pool = None
+
+        self.speaker_diarize = SpeakerDiarization()
 
         self.audio_feature = None
         self.audio_feature_mean = None
@@ -330,5 +334,15 @@ class MVectorPredictor:
         return True
 
     def speaker_diarization(self, audio_data, sample_rate=16000, speaker_num=None, search_audio_db=False):
-        raise NotImplementedError('speaker_diarization (predict.py:365-395) is CPU clustering glue outside the '
-                                  'B200 hot path (SURVEY.md 2, row 9); it is a caller of predict_batch')
+        """说话人日志识别 (predict.py:365-395) -> [{'speaker': id or name, 'start': s, 'end': s}, ...]"""
+        input_data = self._load_audio(audio_data=audio_data, sample_rate=sample_rate)
+        segments = self.speaker_diarize.segments_audio(input_data)
+        features = self.predict_batch([seg[2] for seg in segments], sample_rate=sample_rate)
+        labels, spk_center_embeddings = self.speaker_diarize.clustering(features, speaker_num=speaker_num)
+        outputs = self.speaker_diarize.postprocess(segments, labels)
+        if search_audio_db:
+            assert self.audio_feature is not None, "数据库中没有音频数据，请先指定说话人特征数据库或者注册说话人"
+            names = self.__retrieval(np_feature=spk_center_embeddings)
+            outputs = [{'speaker': names[o['speaker']][0] if names[o['speaker']][0] else f"陌生人{o['speaker']}",
+                        'start': o['start'], 'end': o['end']} for o in outputs]
+        return outputs
