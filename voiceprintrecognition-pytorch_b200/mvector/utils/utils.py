@@ -1,53 +1,56 @@
-"""Config helpers.  Mirrors mvector/utils/utils.py:9-54 (print_arguments, add_arguments, Dict/dict_to_object)."""
+"""Config helpers with the reference's names and behaviour (mvector/utils/utils.py:9-54): ``print_arguments`` logs an
+argparse namespace and/or a (up to three levels deep) config dict, ``add_arguments`` registers one CLI flag,
+``dict_to_object`` turns nested dicts into attribute-accessible ``Dict`` objects."""
 from loguru import logger
+
+_RULE = '-' * 48
+_TRUE = frozenset(('y', 'yes', 't', 'true', 'on', '1'))
+_FALSE = frozenset(('n', 'no', 'f', 'false', 'off', '0'))
+
+
+def _log_tree(node, depth=0, max_depth=2):
+    """Nested dict -> one log line per leaf, tab-indented; dicts below max_depth are printed inline like the reference."""
+    for key, value in node.items():
+        if isinstance(value, dict) and depth < max_depth:
+            logger.info('\t' * depth + f'{key}:')
+            _log_tree(value, depth + 1, max_depth)
+        else:
+            logger.info('\t' * depth + f'{key}: {value}')
 
 
 def print_arguments(args=None, configs=None, title=None):
     if args:
         logger.info('----------- 额外配置参数 -----------')
-        for arg, value in sorted(vars(args).items()):
-            logger.info('%s: %s' % (arg, value))
-        logger.info('------------------------------------------------')
+        for name in sorted(vars(args)):
+            logger.info('%s: %s' % (name, getattr(args, name)))
+        logger.info(_RULE)
     if configs:
         logger.info(f'----------- {title or "配置文件参数"} -----------')
-        for a, v in configs.items():
-            if isinstance(v, dict):
-                logger.info(f'{a}:')
-                for a1, v1 in v.items():
-                    if isinstance(v1, dict):
-                        logger.info(f'\t{a1}:')
-                        for a2, v2 in v1.items():
-                            logger.info(f'\t\t{a2}: {v2}')
-                    else:
-                        logger.info(f'\t{a1}: {v1}')
-            else:
-                logger.info(f'{a}: {v}')
-        logger.info('------------------------------------------------')
+        _log_tree(configs)
+        logger.info(_RULE)
 
 
-def _strtobool(v):
-    v = str(v).lower()
-    if v in ('y', 'yes', 't', 'true', 'on', '1'):
+def _to_bool(text):
+    word = str(text).lower()
+    if word in _TRUE:
         return 1
-    if v in ('n', 'no', 'f', 'false', 'off', '0'):
+    if word in _FALSE:
         return 0
-    raise ValueError(f'invalid truth value {v!r}')
+    raise ValueError(f'invalid truth value {text!r}')
 
 
 def add_arguments(argname, type, default, help, argparser, **kwargs):
-    type = _strtobool if type == bool else type
-    argparser.add_argument('--' + argname, default=default, type=type, help=help + ' 默认: %(default)s.', **kwargs)
+    argparser.add_argument('--' + argname, default=default, type=_to_bool if type == bool else type,
+                           help=help + ' 默认: %(default)s.', **kwargs)
 
 
 class Dict(dict):
-    __setattr__ = dict.__setitem__
+    """dict whose keys are also attributes (missing attribute -> KeyError, as in the reference)."""
     __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
 
 
 def dict_to_object(dict_obj):
-    if not isinstance(dict_obj, dict):
-        return dict_obj
-    inst = Dict()
-    for k, v in dict_obj.items():
-        inst[k] = dict_to_object(v)
-    return inst
+    if isinstance(dict_obj, dict):
+        return Dict((k, dict_to_object(v)) for k, v in dict_obj.items())
+    return dict_obj
