@@ -316,3 +316,47 @@ def test_energy_vad_and_diarization_segments():
     assert all(c[2].shape[0] == 24000 for c in chunks) and len(chunks) >= 6
     with pytest.raises(AssertionError):                       # < 5 s of speech: the reference refuses too
         SpeakerDiarization().segments_audio(AudioSegment(x[:40000], 16000))
+
+
+def _header_struct_fields(name):
+    """Field names of ``typedef struct <name> { ... } <name>;`` in include/vpb200.h, in declaration order."""
+    src = open(os.path.join(os.path.dirname(__file__), '..', 'include', 'vpb200.h')).read()
+    body = re.search(r'typedef struct %s \{(.*?)\} %s;' % (name, name), src, re.S).group(1)
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    fields = []
+    for decl in body.split(';'):
+        decl = decl.strip()
+        if not decl:
+            continue
+        ctype, names = decl.split(None, 1)
+        for n in names.split(','):
+            n = n.strip()
+            m = re.match(r'(\w+)\[(\d+)\]', n)
+            fields.append((ctype, m.group(1), int(m.group(2))) if m else (ctype, n, 1))
+    return fields
+
+
+def test_ctypes_structs_follow_the_header_field_by_field():
+    """vp_op / vp_frontend_desc in mvector/_lib.py must list exactly the header's fields, in order, with matching types
+    (the sizeof self-check at load time cannot see two swapped int32 fields)."""
+    from mvector import _lib
+    ctype_of = {'int32_t': ctypes.c_int32, 'int64_t': ctypes.c_int64, 'float': ctypes.c_float}
+    for cname, cls in (('vp_op', _lib.Op), ('vp_frontend_desc', _lib.FrontendDesc)):
+        want = _header_struct_fields(cname)
+        got = list(cls._fields_)
+        assert len(want) == len(got), cname
+        for (ctype, name, count), (pname, ptype) in zip(want, got):
+            assert name == pname, (cname, name, pname)
+            assert ptype == (ctype_of[ctype] * count if count > 1 else ctype_of[ctype]), (cname, name)
+
+
+def test_golden_fixtures_are_complete_and_small(manifest):
+    gdir = os.path.join(os.path.dirname(__file__), 'golden')
+    total = 0
+    for name in manifest:
+        if name.startswith('_'):
+            continue
+        path = os.path.join(gdir, name + '.npz')
+        assert os.path.exists(path), f'{name}.npz is listed in manifest.json but missing'
+        total += os.path.getsize(path)
+    assert total < 24 << 20, 'golden fixtures are meant to stay small (they travel with every gpurun snapshot)'
