@@ -545,3 +545,40 @@ def test_speaker_diarization_flow(manifest):
     feats = ofe.featurize(xb, ratio, m['preprocess']['feature_method'], m['preprocess']['method_args'])
     ref = om.forward(m['model'], sd, feats, **m['model_args']).numpy()
     assert rel_l2(emb, ref).max() < EMB_TOL
+
+
+@pytest.mark.skipif(os.environ.get('VPB_TEST_EXPERIMENTAL') != '1',
+                    reason='opt-in: experimental cp.async pooling kernels (csrc/pool_v2.cu) staged for round 2')
+def test_experimental_pool_v2_matches_default_kernels():
+    """VPB_POOL_V2=1 must reproduce the default pooling kernels bit for bit (same arithmetic, different staging).  The
+    flag is read once per process, so the flagged run happens in a subprocess."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
+from loguru import logger; logger.remove()
+from oracle import models as om
+from mvector.models import build_model
+from mvector.utils.utils import dict_to_object
+out = {}
+for name, fdim, margs, B, T in (('EcapaTdnn', 80, dict(embd_dim=192), 4, 298), ('TDNN', 80, dict(embd_dim=192), 3, 218),
+                               ('CAMPPlus', 80, dict(embd_dim=192), 2, 298)):
+    sd = om.random_state_dict(name, fdim, seed=3, **margs)
+    m = build_model(fdim, dict_to_object({'model_conf': {'model': name, 'model_args': margs}}))
+    m.load_state_dict({'0.' + k: v for k, v in sd.items()})
+    x = torch.randn(B, T, fdim, generator=torch.Generator().manual_seed(1)) * 2
+    out[name] = m(x.cuda()).cpu().numpy()
+np.savez(sys.argv[1], **out)
+'''
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        for flag in ('0', '1'):
+            path = os.path.join(td, f'emb{flag}.npz')
+            env = dict(os.environ, VPB_POOL_V2=flag)
+            r = subprocess.run([sys.executable, '-c', code, path], env=env, capture_output=True, text=True, timeout=600,
+                               cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            assert r.returncode == 0, r.stderr[-2000:]
+            res[flag] = dict(np.load(path))
+    for k in res['0']:
+        assert np.array_equal(res['0'][k], res['1'][k]), k

@@ -4,6 +4,8 @@
 //                CAM++ StatsPool (campplus.py:27-33), TSTP (pooling.py:140-148), CAM++ context (campplus.py:96-111)
 //   asp_pool   : softmax over time + attentive mean/std (pooling.py:120-126)
 //   ew         : SE excite + residual (ecapa_tdnn.py:84,143; resnet_se.py:40-44), AFF blend (eres2net.py:48-50)
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace vpb {
@@ -77,7 +79,15 @@ __global__ void __launch_bounds__(256) colstats_kernel(const __grid_constant__ S
   }
 }
 
+// VPB_POOL_V2=1 routes the supported shapes to the experimental cp.async variants (pool_v2.cu); default: off.
+static bool pool_v2_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VPB_POOL_V2"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on == 1;
+}
+
 cudaError_t launch_colstats(const StatsParams& p, cudaStream_t stream) {
+  if (pool_v2_enabled() && colstats_v2_supported(p)) return launch_colstats_v2(p, stream);
   dim3 grid((p.C + 31) / 32, p.B);
   colstats_kernel<<<grid, 256, 0, stream>>>(p);
   return cudaGetLastError();
@@ -219,6 +229,7 @@ __global__ void __launch_bounds__(256) asp_pool_smem_kernel(const __grid_constan
 }
 
 cudaError_t launch_asp_pool(const AspParams& p, cudaStream_t stream) {
+  if (pool_v2_enabled() && asp_pool_v2_supported(p)) return launch_asp_pool_v2(p, stream);
   dim3 grid((p.C + 31) / 32, p.B);
   const size_t smem = (size_t)p.T * 32 * 2 * sizeof(float);
   if (smem <= 200 * 1024 && (p.C & 3) == 0 && (p.x_ld & 3) == 0 && (p.x_coff & 3) == 0 && (p.l_ld & 3) == 0 && (p.l_coff & 3) == 0) {
