@@ -126,7 +126,8 @@ enum {                       /* VP_OP_COLSTATS modes (op.mode) */
 enum { VP_EW_GATE_RES = 0, VP_EW_AFF = 1, VP_EW_COPY = 2,
        VP_EW_PAD_COPY = 3 };  /* dst[r, 0:Cout] = (src[r, 0:Cin], zeros): any Cin / in_ld; Cout % 4 == 0 (odd feature dims) */
 enum { VP_BUF_NONE = -1, VP_BUF_INPUT = -2, VP_BUF_OUTPUT = -3 };  /* special values for activation offsets */
-enum { VP_ENGINE_AUTO = 0, VP_ENGINE_FFMA = 1, VP_ENGINE_TC = 2 }; /* vp_op.engine: which conv kernel family */
+enum { VP_ENGINE_AUTO = 0, VP_ENGINE_FFMA = 1, VP_ENGINE_TC = 2,   /* vp_op.engine: which conv kernel family */
+       VP_ENGINE_TC16 = 3 };   /* reported by vp_program_op_info only: TC op routed to the experimental fp16 split */
 
 typedef struct vp_op {
   int32_t kind;
@@ -159,7 +160,13 @@ typedef struct vp_op {
   float   eps;
   int32_t tc_bn;           /* N tile of w_tc: 256 if Cout >= 256 else Cout rounded up to 16 */
   int32_t sum_ld, sum_coff;
-  int32_t reserved[4];
+  /* EXPERIMENTAL (opt-in at run time with VPB_TC_F16=1, ignored otherwise): fp16 two-term image of w for the
+   * kind::f16 variant of the tcgen05 engine.  w_tc16_q = (byte offset in the weight arena >> 4) + 1, 0 = none; layout
+   * [n_tile][k_block of 64][hi|lo][tc_bn rows][64 halves], 16-byte chunks XOR-swizzled by (row & 7); the image holds
+   * w * 2^k, tc16_descale = 2^-k is applied to the accumulator. */
+  int32_t w_tc16_q;
+  float   tc16_descale;
+  int32_t reserved[2];
 } vp_op;
 
 /* Upload the packed fp32 weight arena (host pointer, copied to the device; replaces any previous arena). */

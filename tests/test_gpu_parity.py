@@ -582,3 +582,43 @@ np.savez(sys.argv[1], **out)
             res[flag] = dict(np.load(path))
     for k in res['0']:
         assert np.array_equal(res['0'][k], res['1'][k]), k
+
+
+@pytest.mark.skipif(os.environ.get('VPB_TEST_EXPERIMENTAL') != '1',
+                    reason='opt-in: experimental two-term FP16 split of the tcgen05 engine, staged for round 2')
+def test_experimental_tc_f16_split_parity():
+    """VPB_TC_F16=1 routes the wide pointwise / conv layers to conv_tc_kernel<0, true> (kind::f16, hi/lo fp16 terms).
+    Gate: the same 1e-4 embedding parity against the oracle, and the fp16 engine must actually have run."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
+from loguru import logger; logger.remove()
+from oracle import models as om
+from mvector import _lib as L
+from mvector.models import build_model
+from mvector.utils.utils import dict_to_object
+worst = 0.0
+for name, fdim, margs, B, T in (('EcapaTdnn', 80, dict(embd_dim=192), 8, 298), ('TDNN', 80, dict(embd_dim=192), 8, 218),
+                               ('ResNetSE', 64, dict(embd_dim=192), 2, 151)):
+    sd = om.random_state_dict(name, fdim, seed=3, gain=om.CONDITIONED_GAIN[name], **margs)
+    m = build_model(fdim, dict_to_object({'model_conf': {'model': name, 'model_args': margs}}))
+    m.load_state_dict({'0.' + k: v for k, v in sd.items()})
+    x = torch.randn(B, T, fdim, generator=torch.Generator().manual_seed(1)) * 2
+    ref = om.forward(name, sd, x, **margs).numpy()
+    prog = m.program(B, T)
+    emb = torch.empty(B, m.embd_dim, device='cuda')
+    ops = prog.run_profiled(x.cuda().contiguous(), emb)
+    assert any(o['engine'] == L.ENGINE_TC16 for o in ops), name + ': fp16 engine not selected'
+    got = emb.cpu().numpy()
+    err = float((np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1)).max())
+    print(name, 'rel-L2', err, 'fp16 ops', sum(o['engine'] == L.ENGINE_TC16 for o in ops))
+    worst = max(worst, err)
+assert worst < 1e-4, worst
+print('TC_F16_OK')
+'''
+    env = dict(os.environ, VPB_TC_F16='1')
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=900,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and 'TC_F16_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

@@ -360,3 +360,22 @@ def test_golden_fixtures_are_complete_and_small(manifest):
         assert os.path.exists(path), f'{name}.npz is listed in manifest.json but missing'
         total += os.path.getsize(path)
     assert total < 24 << 20, 'golden fixtures are meant to stay small (they travel with every gpurun snapshot)'
+
+
+def test_pack_tc16_image_roundtrip():
+    """Experimental fp16 split weight image (engine.pack_tc16): hi + lo reproduces W * 2^k to ~2^-22, the layout decodes
+    back through the swizzle, padding rows / columns are zero, descale = 2^-k."""
+    from mvector.engine import pack_tc16, tc_tile_n, unpack_tc16
+    rng = np.random.default_rng(3)
+    for N, K in ((512, 512), (1536, 1536), (192, 200), (128, 72)):
+        W = rng.standard_normal((N, K)) * 0.05
+        bn = tc_tile_n(N, K)
+        img, descale = pack_tc16(W, bn)
+        nt, kb = (N + bn - 1) // bn, (K + 63) // 64
+        assert img.dtype == np.float32 and img.size * 4 == nt * kb * 2 * bn * 128
+        k = -int(round(np.log2(descale)))
+        assert descale == 2.0 ** -k and 2.0 ** 13 < np.abs(W).max() * 2.0 ** k <= 2.0 ** 14
+        hi, lo = unpack_tc16(img, N, K, bn)
+        err = np.abs((hi.astype(np.float64) + lo) * descale - W).max() / np.abs(W).max()
+        assert err < 2.0 ** -21, err
+        assert np.abs(lo).max() <= np.abs(hi).max() * 2.0 ** -10

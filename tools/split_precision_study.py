@@ -2,6 +2,7 @@
 operands of every conv / linear of the oracle forward and accumulating the kept cross terms in fp64.
 
   tf32x3 : hi = tf32(x), lo = tf32(x - hi);  hi*hi + hi*lo + lo*hi          (what conv_tc.cu does today)
+  fp16x2u: like fp16x2 but the ACTIVATIONS are split unscaled (weights still scaled per tensor)
   fp16x2 : per-tensor power-of-two scale s (max|x| * s <= 2^14); hi = fp16(x s), lo = fp16(x s - hi) (subnormals allowed);
            hi*hi + hi*lo + lo*hi, descaled                                      (round-2 candidate: kind::f16 runs at 2x tf32)
   bf16x3 : hi/mid/lo bf16, the six terms of order <= 2                           (for comparison)
@@ -53,6 +54,9 @@ def parts(x, scheme):
     if scheme == 'bf16x3':
         a = r_bf16(x); b = r_bf16(x - a); c = r_bf16(x - a - b)
         return [(0, a), (1, b), (2, c)], 1.0
+    if scheme == 'fp16x2u':                       # unscaled two-term fp16 split (activations): no max|x| needed
+        hi = r_fp16(x)
+        return [(0, hi), (1, r_fp16(x - hi))], 1.0
     if scheme in ('fp16x2', 'fp16x1'):
         s = pow2_scale(x)
         xs = x * s
@@ -73,7 +77,7 @@ class Emulate:
 
         def wrapped(x, w, bias=None, *a, **k):
             xp, dx = parts(x.float(), scheme)
-            wp, dw = parts(w.float(), scheme)
+            wp, dw = parts(w.float(), 'fp16x2' if scheme == 'fp16x2u' else scheme)
             max_order = 0 if len(xp) == 1 else (1 if len(xp) == 2 else 2)
             acc = None
             for ox, xa in xp:
@@ -110,7 +114,7 @@ CASES = {
 
 def main(argv):
     names = argv or ['EcapaTdnn', 'TDNN']
-    schemes = ['tf32x3', 'fp16x2', 'bf16x3', 'tf32x1', 'fp16x1', 'bf16x1']
+    schemes = ['tf32x3', 'fp16x2', 'fp16x2u', 'bf16x3', 'tf32x1', 'fp16x1', 'bf16x1']
     print(f'{"model":10s} ' + ' '.join(f'{s:>9s}' for s in schemes) + '   (max rel-L2 of the embedding vs exact-contraction forward)')
     for name in names:
         fdim, margs, B, T = CASES[name]

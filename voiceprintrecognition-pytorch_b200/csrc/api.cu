@@ -2,6 +2,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -55,6 +56,13 @@ static int fail(vp_handle* h, int code, const char* fmt, ...) {
   } while (0)
 
 static const int FPB = 16;   // frames per front-end CTA
+
+// VPB_TC_F16=1 routes eligible tensor-core convs to the experimental two-term FP16 split (conv_tc.cu); default: off.
+static bool tc16_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VPB_TC_F16"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on == 1;
+}
 
 extern "C" {
 
@@ -433,6 +441,17 @@ int vp_program_create(vp_handle* h, const vp_op* ops, int32_t n_ops, size_t ws_b
       return r;
     }
     p->engines[i] = (o.engine == VP_ENGINE_TC || (o.engine == VP_ENGINE_AUTO && ok)) ? VP_ENGINE_TC : VP_ENGINE_FFMA;
+    // experimental fp16 split: only with VPB_TC_F16=1, only for internal (normalised) activations, never the raw input
+    if (p->engines[i] == VP_ENGINE_TC && tc16_enabled() && o.w_tc16_q > 0 && o.src != VP_BUF_INPUT && conv_tc16_supported(c)) {
+      const int bn = o.tc_bn, nt = (o.Cout + bn - 1) / bn, kb = (c.K + 63) / 64;
+      const size_t off = (size_t)(o.w_tc16_q - 1) << 4, bytes = (size_t)nt * kb * 2 * bn * 128;
+      if (off + bytes > h->weights_bytes || !(o.tc16_descale > 0.f)) {
+        int r = fail(h, VP_ERR_INVALID, "op %d: fp16 weight image out of range", i);
+        delete p;
+        return r;
+      }
+      p->engines[i] = VP_ENGINE_TC16;
+    }
   }
   if (cudaSetDevice(h->device) != cudaSuccess || cudaMalloc(&p->d_ws, p->ws_bytes ? p->ws_bytes : 256) != cudaSuccess) {
     delete p;
@@ -494,7 +513,10 @@ static int run_ops(vp_program* p, const float* feats, float* emb, cudaStream_t s
         if (o.kind == VP_OP_CONV_C1) {
           CUDA_TRY(h, launch_conv_c1(c, st));
         } else {
-          if (p->engines[i] == VP_ENGINE_TC) CUDA_TRY(h, launch_conv_tc(c, st));
+          if (p->engines[i] == VP_ENGINE_TC16)
+            CUDA_TRY(h, launch_conv_tc16(c, reinterpret_cast<const float*>(reinterpret_cast<const char*>(h->d_weights) + ((size_t)(o.w_tc16_q - 1) << 4)),
+                                         o.tc16_descale, st));
+          else if (p->engines[i] == VP_ENGINE_TC) CUDA_TRY(h, launch_conv_tc(c, st));
           else CUDA_TRY(h, launch_conv_ffma(c, st));
         }
         break;

@@ -18,7 +18,10 @@
 //                           bulk-async copy (TMA engine, cp.async.bulk -> UBLKCP) per stage lands B_hi|B_lo
 //   warp 13    MMA issuer : one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8), commits to mbarriers
 // Pipeline: S shared-memory stages (full/empty mbarriers) + 2 TMEM accumulator buffers (tmem_full/tmem_empty).
+#include <cuda_fp16.h>
+
 #include <cstdlib>
+#include <type_traits>
 
 #include "kernels.cuh"
 
@@ -92,6 +95,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, kind::f16 (fp16 operands, UMMA_K = 16, fp32 accumulate) -- experimental two-term FP16 split path
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 (16 B) |
 // SBO = 1024 B (8 rows x 128 B) | version 1 (sm_100) | layout type 2 (SWIZZLE_128B)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
@@ -122,6 +134,7 @@ template <int MODE> struct Slot;
 template <> struct Slot<0> { float4 v[ROWS_PER_THREAD]; };
 template <> struct Slot<1> { float4 v[ROWS_PER_THREAD]; float4 u[ROWS_PER_THREAD]; };
 template <> struct Slot<2> { float4 v[ROWS_PER_THREAD]; float4 ps, ph; uint32_t okmask; };
+struct SlotH { float4 v[ROWS_PER_THREAD]; float4 w[ROWS_PER_THREAD]; };   // F16 path: 8 consecutive K elements per row
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
   asm volatile(
@@ -144,11 +157,19 @@ struct TcArgs {
   int m_tiles, n_tiles, k_blocks;
   int kc, n_chunks;      // K blocks per accumulation chunk / chunks per tile (long-K layers: bounded accumulation length)
   int debug;             // experiments only (VPB_TC_DEBUG): 1 = skip B copies, 2 = skip A global loads, 4 = skip MMAs
+  float descale;         // F16 path only: 1 / (power-of-two scale folded into the fp16 weight image); keep LAST
 };
 
-template <int MODE>
+// F16 = true (experimental, opt-in via VPB_TC_F16=1, MODE 0 only): operands are split into two fp16 terms instead of
+// two tf32 terms -- hi = fp16(x), lo = fp16(x - hi), same three MMAs, kind::f16 at twice the tf32 issue rate; a stage
+// row of 128 B then holds 64 K elements (BKE) and a producer thread moves 8 of them per row (KPT).
+template <int MODE, bool F16 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p,
                                                                  const __grid_constant__ TcArgs a) {
+  static_assert(!F16 || MODE == 0, "the fp16 split path only implements the plain / concat source mode");
+  constexpr int BKE = F16 ? 64 : BK;     // K elements per pipeline stage
+  constexpr int KPT = F16 ? 8 : 4;       // K elements per producer thread and row
+  using SlotT = typename std::conditional<F16, SlotH, Slot<MODE>>::type;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(8) uint64_t bars[2 * 8 + 4];     // full[S], empty[S], tmem_full[2], tmem_empty[2]
@@ -214,10 +235,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     // channel) decomposition of q is kept incrementally -- no integer division per K block (ncu, Res2 convs: the old
     // per-call divisions + 64-bit row arithmetic made the producers instruction-issue bound at N = 64).
     int g_tl = 0, g_kb = 0;                    // tile (local index) and K block of the next item to gather
-    int g_k = chunk * 4;                       // this thread's first k of that K block
+    int g_k = chunk * KPT;                     // this thread's first k of that K block
     int g_ci = 0, g_kt = 0, g_kf = 0;          // channel / tap position of g_k
     auto cursor_reset = [&]() {
-      g_kb = 0; g_k = chunk * 4; g_ci = g_k; g_kt = 0; g_kf = 0;
+      g_kb = 0; g_k = chunk * KPT; g_ci = g_k; g_kt = 0; g_kf = 0;
       if (!pointwise)
         while (g_ci >= p.CinTot) { g_ci -= p.CinTot; if (++g_kf == p.KF) { g_kf = 0; ++g_kt; } }
     };
@@ -227,8 +248,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       // even a predicated-off consumer stalls on the load's scoreboard and would serialise the loads); add / BN-ReLU
       // prologue are applied in publish().  MODE 0: plain or channel-concat source, 3 K blocks in flight; MODE 1: second
       // source added (x_i + y_{i-1}); MODE 2: per-channel affine(+ReLU) prologue; 2 K blocks in flight for 1 and 2.
-      Slot<MODE> sl0, sl1, sl2;
-      auto gather = [&](Slot<MODE>& sl) {
+      SlotT sl0, sl1, sl2;
+      auto gather = [&](SlotT& sl) {
         if (g_kb == 0) {                       // cursor entered a new tile: decode its 4 rows
           const int g = cluster_id + g_tl * n_clusters;
           const int m0 = ((g / a.n_tiles) * (int)C + (int)crank) * BM;
@@ -265,6 +286,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           const uint32_t r = (uint32_t)(rows[i].base + ti * p.Fin + fi);       // source row index (< 2^31 rows)
           sl.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ok) sl.v[i] = __ldg(reinterpret_cast<const float4*>(base + (uint64_t)r * ldb));
+          if constexpr (F16) {
+            sl.w[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) sl.w[i] = __ldg(reinterpret_cast<const float4*>(base + (uint64_t)r * ldb + 16));
+          }
           if constexpr (MODE == 1) {
             sl.u[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ok)
@@ -278,16 +303,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           ++g_tl;
           cursor_reset();
         } else {
-          g_k += BK;
-          g_ci += BK;
+          g_k += BKE;
+          g_ci += BKE;
           if (!pointwise)
             while (g_ci >= p.CinTot) { g_ci -= p.CinTot; if (++g_kf == p.KF) { g_kf = 0; ++g_kt; } }
         }
       };
-      constexpr int DEPTH = (MODE == 0) ? 3 : 2;
+      constexpr int DEPTH = (MODE == 0 && !F16) ? 3 : 2;
       int p_s = 0;
       uint32_t p_ph = 0;
-      auto publish = [&](int q, Slot<MODE>& sl) {
+      auto publish = [&](int q, SlotT& sl) {
         const int s = p_s;
         const uint32_t ph = p_ph;
         if (++p_s == S) { p_s = 0; p_ph ^= 1u; }
@@ -298,6 +323,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         for (int i = 0; i < ROWS_PER_THREAD; ++i) {
           const int r = r0 + 32 * i;
           const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+          if constexpr (F16) {
+            // 8 consecutive K elements -> one 16-byte chunk of fp16 hi and one of fp16 lo (lo = x - hi, exact in fp32)
+            const float xs[8] = {sl.v[i].x, sl.v[i].y, sl.v[i].z, sl.v[i].w, sl.w[i].x, sl.w[i].y, sl.w[i].z, sl.w[i].w};
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __half2 h = __floats2half2_rn(xs[2 * j], xs[2 * j + 1]);
+              const float2 hf = __half22float2(h);
+              const __half2 l = __floats2half2_rn(xs[2 * j] - hf.x, xs[2 * j + 1] - hf.y);
+              hw[j] = *reinterpret_cast<const uint32_t*>(&h);
+              lw[j] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(hw[0]), "r"(hw[1]), "r"(hw[2]), "r"(hw[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(lw[0]), "r"(lw[1]), "r"(lw[2]), "r"(lw[3]) : "memory");
+            continue;
+          }
           float4 x = sl.v[i];
           if constexpr (MODE == 1) { x.x += sl.u[i].x; x.y += sl.u[i].y; x.z += sl.u[i].z; x.w += sl.u[i].w; }
           if constexpr (MODE == 2) {
@@ -361,7 +402,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       // kind::tf32 instruction descriptor: D=F32 (bit 4), A=B=TF32 (2 at bits 7 and 10), K-major, N>>3 @17, M>>4 @24
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // (kind::f16: A = B = F16 is format code 0 at bits 7 and 10)
+      const uint32_t fmt = F16 ? 0u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       uint32_t ccount = 0;
       int s = 0;
       uint32_t sph = 0;                                       // stage / phase cursors, advanced without divisions
@@ -386,9 +429,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             for (int kc = 0; kc < BK / 8; ++kc) {             // UMMA_K = 8 for tf32 = 32 bytes inside the swizzle row
               const uint64_t dah = smem_desc(a_hi + kc * 32), dal = smem_desc(a_lo + kc * 32);
               const uint64_t dbh = smem_desc(b_hi + kc * 32), dbl = smem_desc(b_lo + kc * 32);
-              umma_tf32(d, dal, dbh, idesc, (kb != kb0) || (kc != 0));
-              umma_tf32(d, dah, dbl, idesc, 1);
-              umma_tf32(d, dah, dbh, idesc, 1);
+              if constexpr (F16) {                              // UMMA_K = 16 halves = the same 32 bytes of the row
+                umma_f16(d, dal, dbh, idesc, (kb != kb0) || (kc != 0));
+                umma_f16(d, dah, dbl, idesc, 1);
+                umma_f16(d, dah, dbh, idesc, 1);
+              } else {
+                umma_tf32(d, dal, dbh, idesc, (kb != kb0) || (kc != 0));
+                umma_tf32(d, dah, dbl, idesc, 1);
+                umma_tf32(d, dah, dbh, idesc, 1);
+              }
             }
             if (C > 1) umma_commit_mcast(empty0 + 8 * s, cmask);   // frees the stage in every CTA of the cluster
             else umma_commit(empty0 + 8 * s);                 // frees the smem stage when these MMAs retire
@@ -490,6 +539,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             v[i] = *reinterpret_cast<const float4*>(pad + (rsub + 4 * i) * 36 + cg);
+            if constexpr (F16) { v[i].x *= a.descale; v[i].y *= a.descale; v[i].z *= a.descale; v[i].w *= a.descale; }
             v[i].x += b4.x; v[i].y += b4.y; v[i].z += b4.z; v[i].w += b4.w;
           }
           if (p.ubias) {
@@ -591,19 +641,23 @@ bool conv_tc_supported(const ConvParams& p) {
   return true;
 }
 
-cudaError_t launch_conv_tc(const ConvParams& p, cudaStream_t stream) {
+// f16 = true: experimental two-term FP16 split (conv_tc_kernel<0, true>); w_img is then the fp16 weight image and
+// descale the inverse of the power-of-two scale folded into it.
+static cudaError_t launch_conv_tc_impl(const ConvParams& p, const float* w_img, bool f16, float descale, cudaStream_t stream) {
   using namespace tc;
   TcArgs a;
-  a.w_tc = p.w_tc;
+  a.w_tc = w_img;
+  a.descale = descale;
   a.BN = p.tc_bn;
+  const int bke = f16 ? 64 : BK;
   const int stage_bytes = 2 * A_TILE + 2 * a.BN * 128;
   a.stages = SMEM_BUDGET / stage_bytes;
   if (a.stages > 8) a.stages = 8;
   if (a.stages < 2) return cudaErrorInvalidConfiguration;
   a.m_tiles = (p.M + BM - 1) / BM;
   a.n_tiles = (p.N + a.BN - 1) / a.BN;
-  a.k_blocks = (p.K + BK - 1) / BK;
-  a.kc = tc_chunked(p.K) ? KC_BLOCKS : a.k_blocks;
+  a.k_blocks = (p.K + bke - 1) / bke;
+  a.kc = tc_chunked(p.K) ? KC_BLOCKS * BK / bke : a.k_blocks;      // chunks of 512 K elements either way
   a.n_chunks = (a.k_blocks + a.kc - 1) / a.kc;
   // accumulator regions [acc*BN, +BN) (+ running sum at 2*BN when chunked); tcgen05.ld reads 32 columns at a time, so
   // the last 32-column read of the last region must stay inside the allocation
@@ -622,6 +676,7 @@ cudaError_t launch_conv_tc(const ConvParams& p, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -652,11 +707,30 @@ cudaError_t launch_conv_tc(const ConvParams& p, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e;
-  if (p.pre_s != nullptr) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, p, a);
+  if (f16) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, true>, p, a);
+  else if (p.pre_s != nullptr) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, p, a);
   else if (p.src2_mode == VP_SRC2_ADD) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, p, a);
   else e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<0>, p, a);
   if (e != cudaSuccess) return e;
   return cudaGetLastError();
+}
+
+cudaError_t launch_conv_tc(const ConvParams& p, cudaStream_t stream) {
+  return launch_conv_tc_impl(p, p.w_tc, false, 1.f, stream);
+}
+
+// Experimental FP16-split engine (opt-in, see api.cu): plain / concat source only, 8-element channel granularity, and
+// the same tiling rule as the tf32 image.  The activations are split unscaled (fp16 range: |x| < 65504), so the caller
+// must not route the raw program input (un-normalised features) through it.
+bool conv_tc16_supported(const ConvParams& p) {
+  if (!conv_tc_supported(p)) return false;
+  if (p.pre_s != nullptr || p.src2_mode == VP_SRC2_ADD) return false;
+  if ((p.Cin & 7) || (p.CinTot & 7) || (p.K & 7)) return false;
+  return p.N >= 128;                                  // narrow layers are not tensor bound: nothing to gain
+}
+
+cudaError_t launch_conv_tc16(const ConvParams& p, const float* w_tc16, float descale, cudaStream_t stream) {
+  return launch_conv_tc_impl(p, w_tc16, true, descale, stream);
 }
 
 }  // namespace vpb

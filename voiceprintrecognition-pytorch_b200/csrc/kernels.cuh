@@ -57,6 +57,9 @@ cudaError_t launch_ew(const EwParams& p, cudaStream_t stream);
 // tcgen05 engine (conv_tc.cu)
 bool conv_tc_supported(const ConvParams& p);
 cudaError_t launch_conv_tc(const ConvParams& p, cudaStream_t stream);
+// experimental two-term FP16 split (opt-in, VPB_TC_F16=1)
+bool conv_tc16_supported(const ConvParams& p);
+cudaError_t launch_conv_tc16(const ConvParams& p, const float* w_tc16, float descale, cudaStream_t stream);
 
 // opt-in experimental variants (pool_v2.cu, VPB_POOL_V2=1)
 bool asp_pool_v2_supported(const AspParams& p);

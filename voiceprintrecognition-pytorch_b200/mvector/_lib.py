@@ -16,7 +16,7 @@ STATS_MEAN, STATS_MEAN_STD_CLAMP, STATS_MEAN_STD_UNBIASED, STATS_MEAN_STD_TSTP, 
 STATS_MEAN_VAR_UNBIASED = 5
 EW_GATE_RES, EW_AFF, EW_COPY, EW_PAD_COPY = 0, 1, 2, 3
 BUF_NONE, BUF_INPUT, BUF_OUTPUT = -1, -2, -3
-ENGINE_AUTO, ENGINE_FFMA, ENGINE_TC = 0, 1, 2
+ENGINE_AUTO, ENGINE_FFMA, ENGINE_TC, ENGINE_TC16 = 0, 1, 2, 3
 
 
 class FrontendDesc(C.Structure):
@@ -37,7 +37,7 @@ class Op(C.Structure):
                                             'KT', 'KF', 'sT', 'sF', 'dT', 'dF', 'padT', 'padF', 'pad_mode',
                                             'w_ld', 'pre_relu', 'act', 'act2', 'seg_len', 'n_seg')]
                 + [('eps', C.c_float), ('tc_bn', C.c_int32), ('sum_ld', C.c_int32), ('sum_coff', C.c_int32),
-                   ('reserved', C.c_int32 * 4)])
+                   ('w_tc16_q', C.c_int32), ('tc16_descale', C.c_float), ('reserved', C.c_int32 * 2)])
 
 
 class VpError(RuntimeError):

@@ -5,6 +5,7 @@ torch is used for device memory, streams and (multi-GPU) torch.distributed only;
 libvpb200.so.
 """
 import ctypes as C
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -13,6 +14,7 @@ import torch
 from . import _lib as L
 
 ALIGN = 256  # bytes; every workspace buffer / weight tensor starts on a 256 B boundary
+TC_F16 = os.environ.get('VPB_TC_F16', '0') == '1'   # experimental fp16 split engine (conv_tc.cu); default off
 
 
 def _check(handle, rc):
@@ -87,6 +89,10 @@ class WeightArena:
             img, bn = pack_tc(W2d)
             d['w_tc'] = self.add(name + '.tc', img)
             d['tc_bn'] = bn
+            if TC_F16 and W2d.shape[0] >= 128 and W2d.shape[1] >= 8 and W2d.shape[1] % 8 == 0:      # experimental fp16 split image (opt-in)
+                img16, descale = pack_tc16(W2d, bn)
+                d['w_tc16'] = self.add(name + '.tc16', img16)
+                d['tc16_descale'] = descale
         return d
 
     def blob(self):
@@ -126,6 +132,41 @@ def pack_tc(W):
     out = np.empty_like(img)
     out[:, :, :, r, c ^ (r & 7), :] = img[:, :, :, r, c, :]
     return np.ascontiguousarray(out).reshape(-1), bn
+
+
+def pack_tc16(W, bn):
+    """[N, K] -> (image viewed as float32, descale) for the experimental kind::f16 path of conv_tc.cu.
+
+    The image holds W * 2^k (k chosen so that max|W| 2^k <= 2^14) as two fp16 terms hi = fp16(.), lo = fp16(. - hi),
+    tiled [n_tiles, k_blocks of 64, 2 (hi|lo), bn rows, 64 halves] with the 16-byte chunks (8 halves) of every 128-byte
+    row XOR-swizzled by (row & 7); descale = 2^-k.  Rows >= N / columns >= K are zero."""
+    N, K = W.shape
+    nt, kb = (N + bn - 1) // bn, (K + 63) // 64
+    wmax = float(np.abs(W).max())
+    k = int(np.floor(np.log2(2.0 ** 14 / wmax))) if wmax > 0 else 0
+    Wp = np.zeros((nt * bn, kb * 64), dtype=np.float32)
+    Wp[:N, :K] = (W * 2.0 ** k).astype(np.float32)
+    hi = Wp.astype(np.float16)
+    lo = (Wp - hi.astype(np.float32)).astype(np.float16)
+    img = np.stack([hi, lo], axis=0).reshape(2, nt, bn, kb, 8, 8)          # [p, nt, r, kb, chunk, 8 halves]
+    img = img.transpose(1, 3, 0, 2, 4, 5)                                  # [nt, kb, p, r, chunk, 8]
+    r = np.arange(bn)[:, None]
+    c = np.arange(8)[None, :]
+    out = np.empty_like(img)
+    out[:, :, :, r, c ^ (r & 7), :] = img[:, :, :, r, c, :]
+    return np.ascontiguousarray(out).reshape(-1).view(np.float32), float(2.0 ** -k)
+
+
+def unpack_tc16(img, N, K, bn):
+    """Inverse of pack_tc16 (tests): -> (hi, lo) float32 [N, K] of the scaled weights."""
+    nt, kb = (N + bn - 1) // bn, (K + 63) // 64
+    a = np.ascontiguousarray(img).view(np.float16).reshape(nt, kb, 2, bn, 8, 8)
+    r = np.arange(bn)[:, None]
+    c = np.arange(8)[None, :]
+    un = np.empty_like(a)
+    un[:, :, :, r, c, :] = a[:, :, :, r, c ^ (r & 7), :]
+    un = un.transpose(2, 0, 3, 1, 4, 5).reshape(2, nt * bn, kb * 64).astype(np.float32)
+    return un[0, :N, :K], un[1, :N, :K]
 
 
 class View:
@@ -243,6 +284,8 @@ class PlanBuilder:
         o.KT, o.KF, o.sT, o.sF, o.dT, o.dF, o.padT, o.padF, o.pad_mode = KT, KF, sT, sF, dT, dF, padT, padF, pad_mode
         if isinstance(w, dict):            # packed by WeightArena.add_conv: plain + optional tensor-core image
             o.w, o.w_tc, o.tc_bn = w['w'], w.get('w_tc', -1), w.get('tc_bn', 0)
+            if 'w_tc16' in w:
+                o.w_tc16_q, o.tc16_descale = (w['w_tc16'] >> 4) + 1, w['tc16_descale']
         else:
             o.w = w
         o.w_ld, o.bias = w_ld, bias
