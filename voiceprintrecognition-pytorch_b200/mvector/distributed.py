@@ -4,6 +4,11 @@ all-gather of the per-rank ``[B/R, embd]`` fp32 outputs so that every rank ends 
 order.  Ragged batches keep the reference's single-batch semantics (predict.py:244-258: pad to the longest item of the
 WHOLE batch, T and the CMN mean follow that padding) by padding every shard to the global ``Lmax`` on the host.
 
+One front-end is NOT shard-invariant: torchaudio's MFCC clamps to (max over the whole call) - top_db, so a sharded call
+would clamp against the shard's maximum instead of the batch's.  Matching the single-process result needs one extra
+all-reduce(MAX) of that scalar between the mel stage and the DCT; until that exists, shard MFCC configurations only when
+the per-shard clamp is acceptable (Fbank / MelSpectrogram / Spectrogram have no cross-utterance term).
+
 torch.distributed (NCCL on GPUs, gloo in the CPU tests) is plumbing only; the compute is ``embed_fn``."""
 import numpy as np
 import torch
