@@ -98,7 +98,7 @@ int vp_mfcc(vp_handle* h, const float* wave, int32_t B, int32_t Lpad, const int3
             float* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
- * Backbone (seam 2).  The host (Python mirror of mvector/models/*.py) lowers a model + a concrete (B, T) to a
+ * Backbone (seam 2).  The host (Python mirror of the reference's mvector/models modules) lowers a model + a concrete (B, T) to a
  * straight-line program of fused ops over a workspace arena; weights live in one packed arena uploaded once.
  * Activations are channel-last: 1-D maps are [B, T, C], 2-D maps are [B, T, F, C] (T = time = conv2d W axis,
  * F = frequency = conv2d H axis of the reference's [B, C, F, T]).

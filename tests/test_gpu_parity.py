@@ -622,3 +622,35 @@ print('TC_F16_OK')
     r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=900,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0 and 'TC_F16_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.skipif(os.environ.get('VPB_TEST_EXPERIMENTAL') != '1',
+                    reason='opt-in: pure-C host example (examples/embed_from_c.c) has not been run on hardware yet')
+def test_c_host_example_matches_python_host(tmp_path):
+    """The same exported program through examples/embed_from_c.c (C, cudart only) and through the Python host."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from tools import export_program as ex
+    from oracle import models as om
+    margs = dict(embd_dim=192)
+    sd = om.random_state_dict('EcapaTdnn', 80, seed=2, **margs)
+    model = _model('EcapaTdnn', 80, margs, sd)
+    B, T = 8, 298
+    path = str(tmp_path / 'ecapa.vpb')
+    ex.export(model, B, T, path)
+    feats = (torch.randn(B, T, 80, generator=torch.Generator().manual_seed(4)) * 2).contiguous()
+    feats.numpy().tofile(str(tmp_path / 'feats.f32'))
+    libdir = os.path.join(root, 'voiceprintrecognition-pytorch_b200')
+    exe = str(tmp_path / 'embed_from_c')
+    r = subprocess.run(['gcc', '-O1', '-I', os.path.join(root, 'include'), '-I', '/usr/local/cuda/include',
+                        os.path.join(root, 'examples', 'embed_from_c.c'), '-o', exe, '-L', libdir, '-lvpb200',
+                        '-L', '/usr/local/cuda/lib64', '-lcudart', '-lm', '-Wl,-rpath,' + libdir],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, path, str(tmp_path / 'feats.f32'), str(tmp_path / 'emb.f32')], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = np.fromfile(str(tmp_path / 'emb.f32'), dtype=np.float32).reshape(B, 192)
+    ref = model(feats.cuda()).cpu().numpy()
+    assert np.array_equal(got, ref)                  # same kernels, same program -> bit identical

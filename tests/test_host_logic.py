@@ -379,3 +379,41 @@ def test_pack_tc16_image_roundtrip():
         err = np.abs((hi.astype(np.float64) + lo) * descale - W).max() / np.abs(W).max()
         assert err < 2.0 ** -21, err
         assert np.abs(lo).max() <= np.abs(hi).max() * 2.0 ** -10
+
+
+def test_program_export_roundtrip_and_c_host_builds(tmp_path):
+    """tools/export_program.py writes (ops, weights) for a C host; examples/embed_from_c.c is a pure-C client of
+    include/vpb200.h: the file round-trips, the example compiles as C against the header, and without a GPU it fails
+    loudly (no CPU path)."""
+    import shutil
+    import subprocess
+    root = os.path.join(os.path.dirname(__file__), '..')
+    sys_path_added = root not in __import__('sys').path
+    if sys_path_added:
+        __import__('sys').path.insert(0, root)
+    from tools import export_program as ex
+    from mvector.models import build_model
+    from mvector.utils.utils import dict_to_object
+    from oracle import models as om
+    margs = dict(embd_dim=32, channels=64)
+    model = build_model(80, dict_to_object({'model_conf': {'model': 'TDNN', 'model_args': margs}}))
+    model.load_state_dict({'0.' + k: v for k, v in om.random_state_dict('TDNN', 80, seed=1, **margs).items()})
+    path = str(tmp_path / 'tdnn.vpb')
+    pb, blob = ex.export(model, 3, 90, path)
+    back = ex.load(path)
+    assert (back['B'], back['T'], back['F'], back['embd_dim']) == (3, 90, 80, 32)
+    assert back['input_floats'] == 3 * 90 * 80 and back['output_floats'] == 3 * 32
+    assert np.array_equal(back['weights'], blob)
+    assert len(back['ops']) == len(pb.ops) and all(bytes(a) == bytes(b) for a, b in zip(back['ops'], pb.ops))
+    if shutil.which('gcc') is None or not os.path.exists('/usr/local/cuda/include/cuda_runtime_api.h'):
+        pytest.skip('no C toolchain / CUDA headers here')
+    libdir = os.path.abspath(os.path.join(root, 'voiceprintrecognition-pytorch_b200'))
+    exe = str(tmp_path / 'embed_from_c')
+    r = subprocess.run(['gcc', '-O1', '-Wall', '-Werror', '-I', os.path.join(root, 'include'), '-I', '/usr/local/cuda/include',
+                        os.path.join(root, 'examples', 'embed_from_c.c'), '-o', exe, '-L', libdir, '-lvpb200',
+                        '-L', '/usr/local/cuda/lib64', '-lcudart', '-lm', '-Wl,-rpath,' + libdir],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, path], capture_output=True, text=True)
+        assert r.returncode == 3 and 'no CPU path' in r.stderr
