@@ -407,7 +407,8 @@ def test_program_export_roundtrip_and_c_host_builds(tmp_path):
     assert len(back['ops']) == len(pb.ops) and all(bytes(a) == bytes(b) for a, b in zip(back['ops'], pb.ops))
     if shutil.which('gcc') is None or not os.path.exists('/usr/local/cuda/include/cuda_runtime_api.h'):
         pytest.skip('no C toolchain / CUDA headers here')
-    libdir = os.path.abspath(os.path.join(root, 'voiceprintrecognition-pytorch_b200'))
+    import __graft_entry__ as ge
+    libdir = os.path.dirname(os.path.abspath(ge.build()))           # builds libvpb200.so when it is missing / stale
     exe = str(tmp_path / 'embed_from_c')
     r = subprocess.run(['gcc', '-O1', '-Wall', '-Werror', '-I', os.path.join(root, 'include'), '-I', '/usr/local/cuda/include',
                         os.path.join(root, 'examples', 'embed_from_c.c'), '-o', exe, '-L', libdir, '-lvpb200',
