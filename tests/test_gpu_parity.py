@@ -654,3 +654,19 @@ def test_c_host_example_matches_python_host(tmp_path):
     got = np.fromfile(str(tmp_path / 'emb.f32'), dtype=np.float32).reshape(B, 192)
     ref = model(feats.cuda()).cpu().numpy()
     assert np.array_equal(got, ref)                  # same kernels, same program -> bit identical
+
+
+@pytest.mark.skipif(os.environ.get('VPB_TEST_EXPERIMENTAL') != '1',
+                    reason='opt-in: experimental cp.async ring of the tcgen05 A producers, staged for round 2')
+def test_experimental_tc_ring_parity():
+    """VPB_TC_RING=1 (conv_tc_kernel<MODE, false, true>): the op-level engine tests and the model parity tests must pass
+    unchanged -- the ring only changes how the A tile reaches shared memory."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VPB_TC_RING='1')
+    env.pop('VPB_TEST_EXPERIMENTAL', None)
+    r = subprocess.run([sys.executable, '-m', 'pytest', '-q', '-m', 'gpu', '-p', 'no:cacheprovider', 'tests/test_gpu_conv_engines.py',
+                        'tests/test_gpu_parity.py', '-k', 'tc_engine or small_models or full_size'],
+                       env=env, cwd=root, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
