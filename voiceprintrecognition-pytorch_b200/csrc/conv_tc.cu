@@ -787,11 +787,18 @@ static cudaError_t launch_conv_tc_impl(const ConvParams& p, const float* w_img, 
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
     if (e != cudaSuccess) return e;
     configured = true;
+  }
+  if (f16 || ring) {                       // the opt-in variants are configured only when they are actually selected
+    static bool configured_exp = false;
+    if (!configured_exp) {
+      cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
+      if (e != cudaSuccess) return e;
+      configured_exp = true;
+    }
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
