@@ -1,24 +1,34 @@
 #!/usr/bin/env python
-"""bench.py -- embeddings/sec of the waveform -> Fbank -> EcapaTdnn -> 192-d embedding path (BASELINE.json).
+"""bench.py -- embeddings/sec of the waveform -> front-end -> backbone -> embedding path on the BASELINE.json configs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--config c2|c3|c4|c5] [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-One "step" = one pass of the hot path over one batch: 256 synthetic 3 s @ 16 kHz utterances PER GPU (BASELINE
-configs[1]; weak scaling: the global batch is 256*N, sharded by contiguous utterance ranges, followed by one NCCL
-all-gather of the [256, 192] embeddings so every rank holds all of them).
+Default (what the driver runs): c2 = EcapaTdnn + Fbank-80, 256 x 3 s @ 16 kHz per GPU (BASELINE configs[1]).  The other
+BASELINE configurations are selected with --config:
+    c3  CAM++ + Fbank-80, 256 x 3 s per GPU (global 2048 on 8 GPUs)
+    c4  ResNetSE + MelSpectrogram (README.md:303-311 method_args), 128 x 5 s per GPU
+    c5  ERes2Net 55 M + Fbank-80, ragged 1-10 s (randint(16000, 160001) samples), 64 per GPU (global 256 on 4 GPUs),
+        every shard padded to the GLOBAL longest item (reference single-batch semantics)
+One "step" = one pass of the hot path over one global batch (weak scaling: per-GPU work fixed).  All configs shard by
+contiguous utterance ranges through the product API ``mvector.distributed`` (``gather_embeddings`` /
+``predict_batch_sharded``): one all-gather of the [B/R, 192] embeddings, no other collective.
 
-Timed quantities (all on the device with CUDA events, max over ranks, barrier + synchronize on both sides):
-  value  : whole-job embeddings/s with the waveforms already resident in HBM (vp_embed_wave + all-gather)
-  e2e    : the same through the public API MVectorPredictor.predict_batch(list of host float32 arrays): host staging,
-           pinned H2D copy, kernels, D2H of the embeddings (+ all-gather) inside the timed region
-  roofline : the dominant kernel (largest share of device time among the program's ops, measured live with per-op CUDA
-           events by vp_embed_profiled on extra steps after the timed region): algorithmic FLOPs / launch time vs the
-           measured dense bf16 tensor peak of MEASURED_PEAKS.json
-  cpu_baseline : the CPU oracle (port of the reference's predict_batch flow: per-utterance Kaldi fbank, CMN, model in
-           chunks of 32, no_grad) on the box's host cores, bounded sample
-`--impl reference` times that CPU path alone and prints the same JSON line with "impl": "reference".
+Timed quantities (CUDA events on the launching stream, max over ranks, barrier + synchronize on both sides):
+  value    : whole-job embeddings/s with the (padded) waveforms already resident in HBM:
+             MVectorPredictor.embed_device (vp_embed_wave per chunk) + all-gather
+  e2e      : the same through the public API on HOST data -- predict_batch_sharded(list of host float32 arrays): native
+             threaded gather into pinned memory, H2D, kernels, all-gather, D2H -- all inside the timed region
+  roofline : the dominant kernel (largest device-time share among the program's ops, measured live with per-op CUDA
+             events by vp_embed_profiled on extra steps after the timed region): algorithmic FLOPs / its launch time vs
+             the measured dense bf16 tensor peak of MEASURED_PEAKS.json (burst figure: the kernel is timed alone);
+             `whole_step` uses the sustained figure
+  cpu_baseline : the UNMODIFIED reference (baseline/_ref) through its own MVectorPredictor.predict_batch on the box's
+             host cores, bounded sample, separate process (falls back to the oracle port only if baseline/_ref is missing)
+  gpu_eager_baseline : the same reference on the same GPU with stock PyTorch eager kernels (cuDNN / cuBLAS), TF32 as
+             shipped and off, with its parity error against the reference's CPU fp32 result -- context, not the target
+`--impl reference` runs the reference arm alone and prints the same JSON line with "impl": "reference".
 """
 import argparse
 import json
@@ -32,114 +42,164 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BATCH_PER_GPU = 256
-SAMPLES = 48000
-MODEL = 'EcapaTdnn'
-MODEL_ARGS = dict(embd_dim=192, pooling_type='ASP', channels=[512, 512, 512, 512, 1536])
-FBANK_ARGS = dict(sample_frequency=16000, num_mel_bins=80)
-GFLOP_PER_UTT = 3.090          # BASELINE.md section 3 (2 x conv/linear MACs of the reference backbone at T=298)
-N_POOL = 4                     # rotating input batches: 4 x 49 MB = 196 MB > 126 MB L2
+N_POOL = 4                     # rotating input batches: >= 160 MB per GPU > 126 MB L2
+FBANK80 = dict(sample_frequency=16000, num_mel_bins=80)
+MEL64 = dict(sample_rate=16000, n_fft=1024, win_length=1024, hop_length=320, f_min=50.0, f_max=14000.0, n_mels=64)
+
+CONFIGS = {
+    'c2': dict(idx=2, model='EcapaTdnn', margs=dict(embd_dim=192, pooling_type='ASP', channels=[512, 512, 512, 512, 1536]),
+               feature='Fbank', fargs=FBANK80, fdim=80, per_gpu=256, samples=48000, ragged=False, steps=50,
+               metric='embeddings/sec (3s@16kHz) ECAPA-TDNN', ref_sample=64, cpu_sample=32,
+               workload='EcapaTdnn+Fbank80, batch 256 x 3 s @ 16 kHz per GPU (BASELINE configs[1])'),
+    'c3': dict(idx=3, model='CAMPPlus', margs=dict(embd_dim=192), feature='Fbank', fargs=FBANK80, fdim=80, per_gpu=256,
+               samples=48000, ragged=False, steps=30, metric='embeddings/sec (3s@16kHz) CAM++', ref_sample=32, cpu_sample=32,
+               workload='CAM++ +Fbank80, batch 256 x 3 s @ 16 kHz per GPU = 2048 over 8 GPUs (BASELINE configs[2])'),
+    'c4': dict(idx=4, model='ResNetSE', margs=dict(embd_dim=192, pooling_type='ASP'), feature='MelSpectrogram', fargs=MEL64,
+               fdim=64, per_gpu=128, samples=80000, ragged=False, steps=30, metric='embeddings/sec (5s@16kHz) ResNetSE',
+               ref_sample=16, cpu_sample=16,
+               workload='ResNetSE+MelSpectrogram(n_fft 1024, hop 320, 64 mels; README.md:303-311), batch 128 x 5 s @ 16 kHz '
+                        'per GPU (BASELINE configs[3])'),
+    'c5': dict(idx=5, model='ERes2Net', margs=dict(embd_dim=192, m_channels=64, mul_channel=2, expansion=4, base_width=24, scale=3),
+               feature='Fbank', fargs=FBANK80, fdim=80, per_gpu=64, samples=None, ragged=True, steps=10,
+               metric='embeddings/sec (ragged 1-10s@16kHz) ERes2Net-55M', ref_sample=4, cpu_sample=4,
+               workload='ERes2Net 55M +Fbank80, ragged batch randint(16000,160001) samples, 64 per GPU = 256 over 4 GPUs, '
+                        'padded to the global longest item (BASELINE configs[4])'),
+}
 
 
-def bench_config(n_gpus):
-    return {'workload': 'EcapaTdnn+Fbank80, batch 256 x 3 s @ 16 kHz per GPU (BASELINE configs[1])',
-            'global_batch': BATCH_PER_GPU * n_gpus, 'samples_per_utt': SAMPLES, 'frames': 298,
-            'parallelism': f'utterance-sharded x{n_gpus} + all-gather of embeddings',
-            'l2': f'inputs rotate over {N_POOL} distinct batches ({N_POOL * BATCH_PER_GPU * SAMPLES * 4 >> 20} MiB > L2); '
-                  'per-step activation traffic is several GB',
+def bench_config(cfg, n_gpus, lmax):
+    return {'workload': cfg['workload'], 'global_batch': cfg['per_gpu'] * n_gpus, 'samples_per_utt': cfg['samples'] or f'1..10 s, padded to {lmax}',
+            'parallelism': f'utterance-sharded x{n_gpus} (mvector.distributed) + one all-gather of the embeddings',
+            'l2': f'inputs rotate over {N_POOL} distinct batches (> L2); per-step activation traffic is several GB',
             'weights': 'seeded random init + randomised BN statistics (oracle.models.random_state_dict seed 0)',
-            'precision': 'fp32 in/out; tensor-core GEMMs use error-compensated split-TF32 (fp32-grade, 1e-4 parity)'}
+            'precision': 'fp32 in/out; tensor-core GEMMs use error-compensated two-term splits (fp32-grade, 1e-4 parity)'}
 
 
-def synth_waves(n, seed):
+def batch_lens(cfg, n, seed):
+    """Lengths (samples) of a global batch of n utterances."""
+    if not cfg['ragged']:
+        return [cfg['samples']] * n
     import torch
     g = torch.Generator().manual_seed(seed)
-    return torch.randn(n, SAMPLES, generator=g) * 0.1
+    return torch.randint(16000, 160001, (n,), generator=g).tolist()
 
 
-def yml_config():
+def synth_waves(lens, seed):
+    """One seeded randn stream, sigma 0.1 (= -20 dBFS, what _load_audio's normaliser emits); same code as
+    baseline/ref_driver.py so both arms see identical waveforms."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return [(torch.randn(int(n), generator=g) * 0.1).numpy() for n in lens]
+
+
+def yml_config(cfg):
     return {'dataset_conf': {'dataset': {'min_duration': 0.3, 'max_duration': 3, 'sample_rate': 16000,
                                          'use_dB_normalization': False, 'target_dB': -20},
                              'eval_conf': {'batch_size': 16, 'max_duration': 20}},
-            'preprocess_conf': {'use_hf_model': False, 'feature_method': 'Fbank', 'method_args': dict(FBANK_ARGS)},
-            'model_conf': {'model': MODEL, 'model_args': dict(MODEL_ARGS)}}
+            'preprocess_conf': {'use_hf_model': False, 'feature_method': cfg['feature'], 'method_args': dict(cfg['fargs'])},
+            'model_conf': {'model': cfg['model'], 'model_args': dict(cfg['margs'])}}
+
+
+def save_weights(cfg, td):
+    import torch
+    from oracle import models as om
+    gain = getattr(om, 'CONDITIONED_GAIN', {}).get(cfg['model'])
+    kw = dict(gain=gain) if gain is not None else {}
+    sd = om.random_state_dict(cfg['model'], cfg['fdim'], seed=0, **kw, **cfg['margs'])
+    torch.save({'0.' + k: v for k, v in sd.items()}, os.path.join(td, 'model.pth'))
+    return sd
+
+
+def cpu_model():
+    try:
+        with open('/proc/cpuinfo') as f:
+            return next(l.split(':', 1)[1].strip() for l in f if l.startswith('model name'))
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# CPU reference arm (oracle port of the reference's flow)
+# reference arm: the unmodified reference in a separate process (baseline/ref_driver.py)
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_reference_pass(sd, waves):
-    """predict.py:244-264 on CPU: featurizer on the whole list (per-utterance kaldi fbank loop + CMN), model in chunks of
-    32 (the reference's default batch_size).  Under no_grad (the shipped code leaves autograd on; this is the faster,
-    i.e. stronger, baseline)."""
+def ref_available():
+    return os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', 'mvector'))
+
+
+def run_ref_driver(cfg, model_dir, lens, seed, device='cpu', steps=1, warmup=1, budget_s=0.0, tf32=None, mode='predict_batch',
+                   batch_size=32, save_emb=None, timeout=1500):
+    spec = {'configs': yml_config(cfg), 'model_path': model_dir, 'lens': [int(x) for x in lens], 'seed': seed, 'device': device,
+            'steps': steps, 'warmup': warmup, 'budget_s': budget_s, 'tf32': tf32, 'mode': mode, 'batch_size': batch_size,
+            'save_emb': save_emb}
+    with tempfile.NamedTemporaryFile('w', suffix='.json', delete=False) as f:
+        json.dump(spec, f)
+        path = f.name
+    env = {k: v for k, v in os.environ.items() if k not in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'RANK', 'WORLD_SIZE', 'LOCAL_RANK',
+                                                            'MASTER_ADDR', 'MASTER_PORT', 'PYTHONPATH')}
+    if device == 'cpu':
+        env['CUDA_VISIBLE_DEVICES'] = ''
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, 'baseline', 'ref_driver.py'), path], capture_output=True, text=True,
+                           timeout=timeout, env=env, cwd=os.path.join(ROOT, 'baseline'))
+    except subprocess.TimeoutExpired:
+        return {'unavailable': 'reference driver timed out'}
+    finally:
+        os.unlink(path)
+    for ln in reversed(r.stdout.strip().splitlines()):
+        if ln.startswith('{'):
+            return json.loads(ln)
+    return {'unavailable': 'reference driver failed: ' + (r.stderr.strip().splitlines() or ['no output'])[-1][:300]}
+
+
+def port_pass(cfg, sd, waves):
+    """Fallback when baseline/_ref is absent: the oracle port of predict.py:244-264 (kind = "port")."""
+    import numpy as np
     import torch
     from oracle import frontend as ofe
     from oracle import models as om
     with torch.no_grad():
-        feats = ofe.featurize(waves, torch.ones(waves.shape[0]), 'Fbank', FBANK_ARGS)
-        out = [om.forward(MODEL, sd, feats[i:i + 32], **MODEL_ARGS) for i in range(0, feats.shape[0], 32)]
-    return torch.cat(out)
+        x, ratio = ofe.pad_batch(waves)
+        feats = ofe.featurize(x, ratio, cfg['feature'], cfg['fargs'])
+        out = [om.forward(cfg['model'], sd, feats[i:i + 32], **cfg['margs']) for i in range(0, feats.shape[0], 32)]
+    return torch.cat(out).numpy()
 
 
-def pick_cpu_threads(sd, waves):
-    """torchrun pins OMP_NUM_THREADS=1 and oversubscribed hosts are slower with every hardware thread: try the whole
-    machine, half and a quarter of it on one pass each and keep the fastest (the strongest CPU baseline)."""
-    import torch
-    ncpu = os.cpu_count() or 1
-    best, best_t = None, None
-    for n in sorted({ncpu, max(ncpu // 2, 1), max(ncpu // 4, 1)}, reverse=True):
-        torch.set_num_threads(n)
-        cpu_reference_pass(sd, waves[:8])
-        t0 = time.perf_counter()
-        cpu_reference_pass(sd, waves[:16])
-        t = time.perf_counter() - t0
-        if best_t is None or t < best_t:
-            best, best_t = n, t
-    torch.set_num_threads(best)
-    return best
-
-
-def time_cpu_reference(n_utts, budget_s, min_reps=1, warmup=1):
-    import torch
-    from oracle import models as om
-    sd = om.random_state_dict(MODEL, 80, seed=0, **MODEL_ARGS)
-    waves = synth_waves(n_utts, 4321)
-    pick_cpu_threads(sd, waves)
-    for _ in range(warmup):
-        cpu_reference_pass(sd, waves)
-    reps, t0 = 0, time.perf_counter()
-    while True:
-        cpu_reference_pass(sd, waves)
-        reps += 1
-        el = time.perf_counter() - t0
-        if reps >= min_reps and el >= budget_s:
-            break
-    return n_utts * reps / el, reps, el
-
-
-def run_reference_arm(args):
-    import torch
+def run_reference_arm(args, cfg):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n = 64
-    waves = synth_waves(n, 4321)
-    from oracle import models as om
-    sd = om.random_state_dict(MODEL, 80, seed=0, **MODEL_ARGS)
-    cores = pick_cpu_threads(sd, waves)
-    for _ in range(max(args.warmup, 1)):
-        cpu_reference_pass(sd, waves)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_reference_pass(sd, waves)
-    el = time.perf_counter() - t0
-    v = n * args.steps / el
-    sample = f'{n} utterances x 3 s per step (bounded sample of the 256-utterance batch), oracle port of predict_batch, no_grad'
-    line = {'impl': 'reference', 'metric': 'embeddings/sec (3s@16kHz) ECAPA-TDNN', 'value': v, 'unit': 'emb/s',
-            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * el / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': bench_config(args.gpus),
-            'cpu_baseline': {'value': v, 'unit': 'emb/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+    n = cfg['ref_sample']
+    lens = batch_lens(cfg, n, 4321 + cfg['idx'])
+    lmax = max(lens)
+    sample = (f'{n} utterances per step (bounded sample of the {cfg["per_gpu"]}-utterance per-GPU batch'
+              + (f', ragged, padded to {lmax} samples' if cfg['ragged'] else f' x {cfg["samples"] / 16000:.0f} s') + ')')
+    with tempfile.TemporaryDirectory() as td:
+        sd = save_weights(cfg, td)
+        if ref_available():
+            out = run_ref_driver(cfg, td, lens, 4321, device='cpu', steps=args.steps, warmup=max(args.warmup, 1))
+            kind = 'reference'
+            sample += '; unmodified reference MVectorPredictor.predict_batch (baseline/_ref), default batch_size 32, autograd on as shipped'
+        else:
+            out = {'unavailable': 'baseline/_ref missing'}
+        if 'unavailable' in out:
+            import torch
+            kind = 'port'
+            sample += f'; oracle port of predict_batch ({out["unavailable"]})'
+            waves = synth_waves(lens, 4321)
+            torch.set_num_threads(max((os.cpu_count() or 2) // 2, 1))
+            for _ in range(max(args.warmup, 1)):
+                port_pass(cfg, sd, waves)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                port_pass(cfg, sd, waves)
+            el = time.perf_counter() - t0
+            out = {'emb_per_s': n * args.steps / el, 'ms_per_step': 1e3 * el / args.steps, 'threads': torch.get_num_threads(),
+                   'cpu_model': cpu_model()}
+    v = out['emb_per_s']
+    line = {'impl': 'reference', 'metric': cfg['metric'], 'value': v, 'unit': 'emb/s', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': out['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': bench_config(cfg, args.gpus, lmax),
+            'cpu_baseline': {'value': v, 'unit': 'emb/s', 'cores': out.get('threads'), 'kind': kind, 'sample': sample,
+                             'cpu_model': out.get('cpu_model')},
             'e2e': {'value': v, 'unit': 'emb/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
@@ -218,7 +278,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
-def run_gpu_arm(args):
+def run_gpu_arm(args, cfg):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -229,53 +289,63 @@ def run_gpu_arm(args):
     assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback on the product path)'
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+
     def mark(msg):
         if os.environ.get('VPB_BENCH_TRACE'):
-            sys.stderr.write(f'[bench rank {rank} {time.strftime("%H:%M:%S")}] {msg}\n'); sys.stderr.flush()
+            sys.stderr.write(f'[bench rank {rank} {time.strftime("%H:%M:%S")}] {msg}\n')
+            sys.stderr.flush()
     if world > 1:
         import datetime
-        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=300))
         mark('process group up')
     assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world}'
 
     import __graft_entry__ as ge
     ge.build()
-    from mvector.predict import MVectorPredictor
-    from oracle import models as om
-
-    sd = om.random_state_dict(MODEL, 80, seed=0, **MODEL_ARGS)
-    with tempfile.TemporaryDirectory() as td:
-        torch.save({'0.' + k: v for k, v in sd.items()}, os.path.join(td, 'model.pth'))
-        import logging
-        from loguru import logger
-        logger.remove()
-        pred = MVectorPredictor(configs=yml_config(), model_path=td, use_gpu=True)
-    B = BATCH_PER_GPU
-    fz = pred._audio_featurizer
-    T = fz.num_frames(SAMPLES)
-    prog = pred.predictor.program(B, T)
+    from loguru import logger
+    logger.remove()
     from mvector import _lib as L
-    pool_host = [synth_waves(B, 1234 + 100 * rank + i).pin_memory() for i in range(N_POOL)]
-    pool_dev = [w.to(dev) for w in pool_host]
-    # predict_batch input: a list of INDEPENDENTLY allocated pageable numpy arrays (like decoded audio files), not views
-    # of one pinned matrix
-    pool_np = [[np.array(w[i].numpy(), copy=True) for i in range(B)] for w in pool_host]
-    feats = torch.empty(B * T * 80, dtype=torch.float32, device=dev)
-    scratch = torch.empty(max(int(L.lib().vp_frontend_scratch_floats(fz.engine.handle, B, SAMPLES)), 1),
-                          dtype=torch.float32, device=dev)
-    emb = torch.empty(B, 192, dtype=torch.float32, device=dev)
-    emb_all = torch.empty(B * world, 192, dtype=torch.float32, device=dev)
+    from mvector import distributed as mdist
+    from mvector.predict import MVectorPredictor
+    if world > 1:
+        mdist.bind_rank_to_local_cpus(local, int(os.environ.get('LOCAL_WORLD_SIZE', world)))
+
+    td_obj = tempfile.TemporaryDirectory()
+    td = td_obj.name
+    sd = save_weights(cfg, td)
+    pred = MVectorPredictor(configs=yml_config(cfg), model_path=td, use_gpu=True)
+    B = cfg['per_gpu']
+    n_glob = B * world
+    lo, hi = mdist.shard_range(n_glob, rank, world)
+    fz = pred._audio_featurizer
+    D = pred.predictor.embd_dim
+
+    # ---- synthetic pools: every rank knows all lengths (-> global Lmax) but only materialises its own shard
+    pools = []
+    for i in range(N_POOL):
+        lens = batch_lens(cfg, n_glob, 1234 + cfg['idx'] + 17 * i)
+        lmax = max(lens)
+        mine = synth_waves(lens[lo:hi], 1234 + 1000 * cfg['idx'] + 100 * rank + i)
+        xd = torch.zeros(hi - lo, lmax, dtype=torch.float32)
+        for j, w in enumerate(mine):
+            xd[j, :w.shape[0]] = torch.from_numpy(w)
+        # predict_batch_sharded input: the whole list; entries outside this rank's shard are length-only placeholders
+        # (never read: a rank touches only its shard) -- in-shard entries are independently allocated pageable arrays
+        full = [mine[j - lo] if lo <= j < hi else np.empty(lens[j], dtype=np.float32) for j in range(n_glob)]
+        keep = None
+        if cfg['ragged']:                               # mask lengths round(len / Lmax * T) (featurizer.py:82-84), resident too
+            keep = fz.keep_frames(torch.tensor([l / lmax for l in lens[lo:hi]], dtype=torch.float32), fz.num_frames(lmax)).to(dev)
+        pools.append(dict(lens=lens, lmax=lmax, dev=xd.to(dev), host_list=full, mine=mine, keep=keep))
+    lmax0 = pools[0]['lmax']
+    emb_all = torch.empty(n_glob, D, dtype=torch.float32, device=dev)
 
     def step_resident(i):
-        prog.run_wave(pool_dev[i % N_POOL], None, feats, scratch, emb)
-        if world > 1:
-            dist.all_gather_into_tensor(emb_all, emb)
+        p = pools[i % N_POOL]
+        loc = pred.embed_device(p['dev'], keep=p['keep'])
+        return mdist.gather_embeddings(loc, n_glob, out=emb_all)
 
     def step_e2e(i):
-        e = pred.predict_batch(pool_np[i % N_POOL])
-        if world > 1:
-            dist.all_gather_into_tensor(emb_all, torch.from_numpy(e).to(dev))
-        return e
+        return mdist.predict_batch_sharded(pred, pools[i % N_POOL]['host_list'])
 
     def sync_all():
         torch.cuda.synchronize()
@@ -307,37 +377,37 @@ def run_gpu_arm(args):
     ms_res = timed(step_resident, args.steps, args.warmup, clocks)
     clk = clocks.stop() if clocks else None
     mark(f'resident timing done: {ms_res:.2f} ms')
-    if os.environ.get('VPB_E2E_ONLY'):
-        ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
-        if rank == 0:
-            print(json.dumps({'e2e_only': True, 'ms_per_step': ms_e2e / args.steps, 'emb_per_s': B * world * args.steps / (ms_e2e * 1e-3)}))
-        return
     if args.light:
         if rank == 0:
-            print(json.dumps({'light': True, 'ms_per_step': ms_res / args.steps, 'note': 'not a bench value'}))
+            print(json.dumps({'light': True, 'config': args.config, 'ms_per_step': ms_res / args.steps, 'note': 'not a bench value'}))
         if world > 1:
             dist.destroy_process_group()
         return
     ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
-
     mark(f'e2e timing done: {ms_e2e:.2f} ms')
-    # sanity inside the bench: the embeddings of the last step agree with the CPU oracle on 2 utterances
-    if rank == 0:
-        from oracle import frontend as ofe
-        i_last = (args.warmup + args.steps - 1) % N_POOL
-        prog.run_wave(pool_dev[i_last], None, feats, scratch, emb)     # local only: no collective on a single rank
-        torch.cuda.synchronize()
-        ref = om.forward(MODEL, sd, ofe.featurize(pool_host[i_last][:2], None, 'Fbank', FBANK_ARGS), **MODEL_ARGS)
-        err = float(((emb[:2].cpu() - ref).norm(dim=1) / ref.norm(dim=1)).max())
-        assert err < 1e-4, f'parity check inside bench failed: rel-L2 {err}'
+
+    # consistency of the two paths on this rank: resident and host-staged results of the same batch are bit-identical
+    i_chk = 0
+    e_res = step_resident(i_chk).clone()
+    e_host = torch.from_numpy(step_e2e(i_chk)).to(dev)
+    sync_all()
+    assert torch.equal(e_res, e_host), 'resident and host-staged paths disagree'
+
+    T0 = fz.num_frames(lmax0)
+    cb = pred._chunk_size(B, T0)
+    prog = pred.predictor.program(cb, T0)
+    n_chunks = -(-B // cb)
+    fe_launches = 3 if fz.feat_fun.desc.post == 1 else 2
+    launches_per_step = n_chunks * (prog.launches + fe_launches)
 
     # ---- live per-op timing for the roofline (extra steps, not part of `value`) ----
     roof = None
     if rank == 0:
-        fz(pool_dev[0])                        # features for the profiled backbone pass
-        f_in = fz(pool_dev[0]).contiguous()
-        acc = None
-        nprof = 3
+        p0 = pools[0]
+        ratio = torch.tensor([l / p0['lmax'] for l in p0['lens'][lo:hi]], dtype=torch.float32)
+        f_in = fz(p0['dev'][:cb], ratio[:cb] if cfg['ragged'] else None).contiguous()
+        emb = torch.empty(cb, D, dtype=torch.float32, device=dev)
+        acc, nprof = None, 3
         for _ in range(nprof):
             ops = prog.run_profiled(f_in, emb)
             if acc is None:
@@ -352,74 +422,151 @@ def run_gpu_arm(args):
             with open(args.dump_ops, 'w') as f:
                 json.dump(acc, f, indent=0)
         conv = [a for a in acc if a['kind'] == L.OP_CONV and a['K'] > 0]
-        top = max(conv, key=lambda a: a['ms'])
+        # dominant kernel = the (M, N, K, engine) class with the largest total device time in the step
+        classes = {}
+        for a in conv:
+            classes.setdefault((a['M'], a['N'], a['K'], a['engine']), []).append(a['ms'])
+        (tM, tN, tK, teng), tms = max(classes.items(), key=lambda kv: sum(kv[1]))
+        top_ms = sum(tms) / len(tms)
         peaks = {}
         ppath = os.path.join(ROOT, 'MEASURED_PEAKS.json')
         if os.path.exists(ppath):
             with open(ppath) as f:
                 peaks = json.load(f)
-        peak = peaks.get('bf16_tflops_sustained')
-        peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)'
+        peak = peaks.get('bf16_tflops')
+        peak_src = 'MEASURED_PEAKS.json bf16_tflops (burst: the kernel is event-timed alone; of measured)'
+        peak_sus = peaks.get('bf16_tflops_sustained')
         if peak is None:
-            peak, peak_src = 1400.0, 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md; of fallback)'
-        flops = 2.0 * top['M'] * top['N'] * top['K']
-        achieved = flops / (top['ms'] * 1e-3) / 1e12
-        traffic = None
+            peak, peak_src, peak_sus = 1590.0, 'fallback 1.59 PFLOP/s burst (B200_PROFILING.md; of fallback)', 1400.0
+        achieved = 2.0 * tM * tN * tK / (top_ms * 1e-3) / 1e12
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get(f"{top['M']}x{top['N']}x{top['K']}")
+                tj = json.load(f)
+            traffic = tj.get(f'{tM}x{tN}x{tK}')
+            traffic_src = tj.get('source', 'profiles/ (ncu --set full capture of the same kernel and shape; not measured in this run)')
         gemm_ms = sum(a['ms'] for a in conv)
         gemm_flops = sum(2.0 * a['M'] * a['N'] * a['K'] for a in conv)
+        eng_name = {L.ENGINE_TC: 'conv_tc_kernel (tcgen05, split-TF32)', L.ENGINE_TC16: 'conv_tc_kernel (tcgen05, two-term FP16 split)',
+                    L.ENGINE_FFMA: 'conv_ffma_kernel (fp32 FFMA)'}.get(teng, str(teng))
+        step_flops = gemm_flops * n_chunks * world
         roof = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-                'traffic': traffic, 'peak_source': peak_src,
-                'kernel': ('conv_tc (tcgen05 split-TF32)' if top['engine'] == L.ENGINE_TC else 'conv_ffma_kernel<128> (fp32 FFMA)')
-                          + f" M={top['M']} N={top['N']} K={top['K']}",
-                'kernel_ms': top['ms'], 'kernel_share_of_backbone': top['ms'] / total,
+                'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
+                'kernel': f'{eng_name} M={tM} N={tN} K={tK} x{len(tms)} per forward',
+                'kernel_ms': top_ms, 'kernel_share_of_backbone': sum(tms) / total,
                 'all_conv': {'tflops': gemm_flops / (gemm_ms * 1e-3) / 1e12, 'ms': gemm_ms, 'share_of_backbone': gemm_ms / total},
-                'backbone_ms_profiled': total}
+                'backbone_ms_profiled': total,
+                'whole_step': {'tflops': step_flops / (ms_res / args.steps * 1e-3) / 1e12, 'peak': peak_sus * world,
+                               'frac': step_flops / (ms_res / args.steps * 1e-3) / 1e12 / (peak_sus * world),
+                               'peak_source': 'bf16_tflops_sustained x n_gpus (kernels timed inside a long step)'}}
 
     if rank == 0:
-        n_emb = B * world * args.steps
+        n_emb = n_glob * args.steps
         value = n_emb / (ms_res * 1e-3)
         e2e_v = n_emb / (ms_e2e * 1e-3)
-        cpu_v, reps, el = time_cpu_reference(32, budget_s=12.0) if world == 1 else (None, 0, 0.0)
-        cores = torch.get_num_threads()
-        line = {'metric': 'embeddings/sec (3s@16kHz) ECAPA-TDNN', 'value': value, 'unit': 'emb/s', 'n_gpus': world,
+        h2d = (hi - lo) * lmax0 * 4 * world          # every rank copies its zero-padded [B/R, Lmax] shard
+        line = {'metric': cfg['metric'], 'value': value, 'unit': 'emb/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_res / args.steps,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': bench_config(world), 'clocks': clk,
-                'e2e': {'value': e2e_v, 'unit': 'emb/s', 'h2d_bytes_per_step': B * SAMPLES * 4,
-                        'd2h_bytes_per_step': B * 192 * 4, 'ms_per_step': ms_e2e / args.steps,
-                        'api': 'MVectorPredictor.predict_batch(list of 256 host float32 arrays)'},
-                'gpu_launches': args.steps * (prog.launches + 2),
-                'launches_per_step': prog.launches + 2,
-                'roofline': roof,
-                'tensor_frac_whole_step': (value * GFLOP_PER_UTT * 1e9 / 1e12) / (roof['peak'] * world) if roof else None}
-        if cpu_v is not None:
-            line['cpu_baseline'] = {'value': cpu_v, 'unit': 'emb/s', 'cores': cores, 'kind': 'port',
-                                    'sample': f'32 utterances x 3 s, {reps} passes in {el:.1f} s; oracle port of '
-                                              'predict_batch (kaldi fbank per utterance, model chunks of 32, no_grad)'}
+                'config': bench_config(cfg, world, lmax0), 'clocks': clk,
+                'e2e': {'value': e2e_v, 'unit': 'emb/s', 'h2d_bytes_per_step': h2d,
+                        'd2h_bytes_per_step': n_glob * D * 4, 'ms_per_step': ms_e2e / args.steps,
+                        'api': 'mvector.distributed.predict_batch_sharded(MVectorPredictor, list of host float32 arrays) '
+                               '(== MVectorPredictor.predict_batch at 1 GPU)'},
+                'gpu_launches': args.steps * launches_per_step,
+                'launches_per_step': launches_per_step,
+                'roofline': roof}
+        if world == 1 and not args.no_baselines:
+            line.update(side_baselines(cfg, td, sd, pred, dev))
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    td_obj.cleanup()
+
+
+def side_baselines(cfg, td, sd, pred, dev):
+    """cpu_baseline (reference CPU), gpu_eager_baseline (reference on the same GPU, PyTorch eager) and this repo's parity
+    against the reference's CPU fp32 result -- all on the SAME bounded sample, after the timed regions."""
+    import numpy as np
+    import torch
+    out = {}
+    n = cfg['cpu_sample']
+    lens = batch_lens(cfg, n, 4321 + cfg['idx'])
+    seed = 4321
+    lmax = max(lens)
+    what = f'{n} utterances' + (f', ragged, padded to {lmax} samples' if cfg['ragged'] else f' x {cfg["samples"] / 16000:.0f} s')
+    emb_path = os.path.join(td, 'ref_cpu.npy')
+    ref = None
+    if ref_available():
+        r = run_ref_driver(cfg, td, lens, seed, device='cpu', steps=1, warmup=1, budget_s=10.0, save_emb=emb_path)
+        if 'unavailable' not in r:
+            out['cpu_baseline'] = {'value': r['emb_per_s'], 'unit': 'emb/s', 'cores': r['threads'], 'kind': 'reference',
+                                   'cpu_model': r.get('cpu_model'),
+                                   'sample': f'{what}, {r["steps"]} passes in {r["elapsed_s"]:.1f} s; unmodified reference '
+                                             'MVectorPredictor.predict_batch (baseline/_ref) in a separate process, autograd on as shipped'}
+            ref = np.load(emb_path)
+    waves = synth_waves(lens, seed)
+    if ref is None:                                     # baseline/_ref missing: oracle port, labelled as such
+        torch.set_num_threads(max((os.cpu_count() or 2) // 2, 1))
+        port_pass(cfg, sd, waves)
+        t0, reps = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 10.0:
+            ref = port_pass(cfg, sd, waves)
+            reps += 1
+        el = time.perf_counter() - t0
+        out['cpu_baseline'] = {'value': n * reps / el, 'unit': 'emb/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                               'cpu_model': cpu_model(), 'sample': f'{what}, {reps} passes in {el:.1f} s; oracle port of predict_batch'}
+    mine = pred.predict_batch(waves)
+    rel = np.linalg.norm(mine - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    out['parity_vs_reference_cpu'] = {'rel_l2_max': float(rel.max()), 'n': n, 'tolerance': 1e-4,
+                                      'against': out['cpu_baseline']['kind']}
+    assert rel.max() < 1e-4, f'parity check inside bench failed: rel-L2 {rel.max()}'
+    if ref_available():
+        eager = {}
+        full_lens = batch_lens(cfg, cfg['per_gpu'], 1234 + cfg['idx'])
+        torch.cuda.synchronize()
+        for tag, tf32 in (('tf32_as_shipped', None), ('tf32_off', False)):
+            gp = os.path.join(td, f'ref_gpu_{tag}.npy')
+            rs = run_ref_driver(cfg, td, lens, seed, device='cuda', steps=1, warmup=1, tf32=tf32, save_emb=gp)
+            if 'unavailable' in rs:
+                eager[tag] = rs
+                continue
+            g = np.load(gp)
+            err = float((np.linalg.norm(g - ref, axis=1) / np.linalg.norm(ref, axis=1)).max())
+            r1 = run_ref_driver(cfg, td, full_lens, 1234, device='cuda', steps=3, warmup=2, tf32=tf32)
+            r2 = run_ref_driver(cfg, td, full_lens, 1234, device='cuda', steps=5, warmup=2, tf32=tf32, mode='model_only', batch_size=32)
+            r3 = run_ref_driver(cfg, td, full_lens, 1234, device='cuda', steps=5, warmup=2, tf32=tf32, mode='model_only',
+                                batch_size=cfg['per_gpu'])
+            eager[tag] = {'predict_batch_emb_per_s': r1.get('emb_per_s'), 'model_only_bs32_emb_per_s': r2.get('emb_per_s'),
+                          'model_only_full_batch_emb_per_s': r3.get('emb_per_s'), 'rel_l2_vs_reference_cpu': err,
+                          'tf32': rs.get('tf32')}
+        eager['note'] = ('unmodified reference modules on this GPU with PyTorch eager (cuDNN/cuBLAS): predict_batch keeps the '
+                         'Kaldi front-end on the CPU (predict.py:256); model_only = backbone with features resident on the device')
+        out['gpu_eager_baseline'] = eager
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=None)
     ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--light', action='store_true', help='resident-input timing only (for runs under ncu): no e2e / '
-                    'cpu baseline / per-op profile; the JSON line is NOT a bench value')
+                    'baselines / per-op profile; the JSON line is NOT a bench value')
+    ap.add_argument('--no-baselines', action='store_true', help='skip the cpu / gpu-eager reference side runs')
     ap.add_argument('--dump-ops', default=None, help='write the per-op device-time profile (JSON) to this path')
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.steps is None:
+        args.steps = cfg['steps'] if args.impl == 'b200' else 5
     if args.impl == 'reference':
-        run_reference_arm(args)
+        run_reference_arm(args, cfg)
     else:
-        run_gpu_arm(args)
+        run_gpu_arm(args, cfg)
 
 
 if __name__ == '__main__':

@@ -14,8 +14,10 @@
  * Conventions: all tensor arguments are caller-owned DEVICE pointers to float32 (row-major, dense); every call
  * takes the CUDA stream to enqueue on (a cudaStream_t passed as void*, NULL = legacy default stream) and is
  * asynchronous; functions return 0 on success or a VP_ERR_* code, with vp_last_error() giving the message.
- * No hidden device allocation after vp_program_create.  One handle per device; thread-compatible (one
- * thread/stream at a time per handle / program).  There is no CPU fallback anywhere behind this ABI.
+ * No hidden device allocation after vp_program_create.  One handle per device; thread-compatible: ONE thread and ONE
+ * stream at a time per handle -- all programs of a handle share one workspace arena (sized to the largest of them), so
+ * two programs of the same handle must never be in flight on different streams.  There is no CPU fallback anywhere
+ * behind this ABI.
  */
 #ifndef VPB200_H_
 #define VPB200_H_
@@ -27,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VP_ABI_VERSION 2
+#define VP_ABI_VERSION 3
 
 enum {
   VP_OK = 0,
@@ -96,6 +98,17 @@ int vp_melspec(vp_handle* h, const float* wave, int32_t B, int32_t Lpad, const i
                float* scratch, void* stream);
 int vp_mfcc(vp_handle* h, const float* wave, int32_t B, int32_t Lpad, const int32_t* keep_frames, float* feats,
             float* scratch, void* stream);
+
+/* vp_mfcc in two stages, for callers that split ONE reference call over several processes (utterance sharding,
+ * SURVEY.md 8e): the top_db clamp of torchaudio's MFCC uses the maximum over the WHOLE call, so a sharded call computes
+ *   vp_mfcc_mel    : mel dB values of its shard into `scratch`, their maximum into max_out[0] (device float),
+ *   (caller)       : all-reduce(MAX) of that one scalar over the ranks (ncclAllReduce / torch.distributed),
+ *   vp_mfcc_finish : clamp to max_in[0] - top_db, DCT-II, CMN, mask -> feats.
+ * `scratch` (vp_frontend_scratch_floats(B, Lpad) floats) must be left untouched between the two calls.
+ * vp_mfcc == vp_mfcc_mel + vp_mfcc_finish with max_in = max_out. */
+int vp_mfcc_mel(vp_handle* h, const float* wave, int32_t B, int32_t Lpad, float* scratch, float* max_out, void* stream);
+int vp_mfcc_finish(vp_handle* h, int32_t B, int32_t Lpad, const int32_t* keep_frames, float* feats, float* scratch,
+                   const float* max_in, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Backbone (seam 2).  The host (Python mirror of the reference's mvector/models modules) lowers a model + a concrete (B, T) to a
@@ -172,7 +185,9 @@ typedef struct vp_op {
 /* Upload the packed fp32 weight arena (host pointer, copied to the device; replaces any previous arena). */
 int vp_weights_load(vp_handle* h, const void* host_blob, size_t nbytes);
 
-/* Validate + own a program for fixed (B, T): allocates workspace_bytes of device memory once. */
+/* Validate + own a program for fixed (B, T).  Its workspace is the handle's shared arena, grown (after draining the
+ * device) when workspace_bytes exceeds the current arena -- serving ragged lengths therefore costs max, not sum, of the
+ * programs' workspaces, and destroying a program frees host memory only. */
 int vp_program_create(vp_handle* h, const vp_op* ops, int32_t n_ops, size_t workspace_bytes, size_t input_floats,
                       size_t output_floats, vp_program** out);
 void vp_program_destroy(vp_program* p);
@@ -190,6 +205,15 @@ int vp_program_op_info(const vp_program* p, int32_t i, int32_t* kind, int64_t* M
  * staging matrix dst[n, lmax] with n_threads worker threads -- the pad-to-longest loop of predict.py:248-254. */
 int vp_host_gather_pad(const float* const* srcs, const int32_t* lens, int32_t n, int32_t lmax, float* dst,
                        int32_t n_threads);
+/* Staging half of predict_batch (predict.py:244-255) as ONE native call: worker threads gather slices of slice_rows
+ * utterances into the zero-padded PINNED matrix staging[n, lmax]; the calling thread issues
+ * cudaMemcpyAsync(staging slice -> device_dst slice) on copy_stream as soon as a slice is complete, so the H2D transfer
+ * of slice k overlaps the gather of slice k+1.  Returns when the last copy has been ENQUEUED.  device_dst == NULL: gather
+ * only (== vp_host_gather_pad). */
+int vp_host_stage_h2d(const float* const* srcs, const int32_t* lens, int32_t n, int32_t lmax, float* staging,
+                      float* device_dst, int32_t slice_rows, int32_t n_threads, void* copy_stream);
+/* bytes of the handle's shared workspace arena right now */
+size_t vp_workspace_bytes(const vp_handle* h);
 /* number of kernel launches one vp_embed enqueues (bench.py's gpu_launches) */
 int32_t vp_program_launches(const vp_program* p);
 /* debugging / tests: copy a workspace region to a caller device buffer on the stream */

@@ -44,6 +44,52 @@ def _worker(rank, world, port, n):
     dist.destroy_process_group()
 
 
+class _FakePredictor:
+    """Host-side stand-in with the three things predict_batch_sharded touches: configs, _load_audio, _embed_waves."""
+    class _Seg:
+        def __init__(self, x):
+            self.samples = x
+
+    def __init__(self):
+        from mvector.utils.utils import dict_to_object
+        self.configs = dict_to_object({'dataset_conf': {'dataset': {'sample_rate': 16000, 'min_duration': 0.001}}})
+        self.loaded = []
+
+    def _load_audio(self, audio_data, sample_rate=16000):
+        self.loaded.append(len(audio_data))
+        return self._Seg(np.asarray(audio_data, dtype=np.float32))
+
+    def _embed_waves(self, waves, lmax, masked, to_numpy=True, group=None):
+        if not waves:
+            return torch.zeros(0, 4)
+        x = np.zeros((len(waves), lmax), dtype=np.float32)
+        for i, w in enumerate(waves):
+            x[i, :len(w)] = w
+        return _fake_embed(x, np.asarray([len(w) / lmax for w in waves], dtype=np.float32))
+
+
+def _worker_predict(rank, world, port, n):
+    from mvector.distributed import predict_batch_sharded, shard_range
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    rng = np.random.default_rng(1)
+    waves = [rng.standard_normal(int(rng.integers(50, 400))).astype(np.float32) for _ in range(n)]
+    pred = _FakePredictor()
+    got = predict_batch_sharded(pred, waves, as_numpy=False)
+    x, ratio = pad_to_global_max(waves)
+    assert torch.equal(got, _fake_embed(x, ratio))               # global Lmax / ratios although only the shard was staged
+    lo, hi = shard_range(n, rank, world)
+    assert sorted(pred.loaded) == sorted(len(w) for w in waves[lo:hi])     # a rank decodes only its own shard
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_predict_batch_sharded_gloo_world2_and_more_ranks_than_items():
+    mp.spawn(_worker_predict, args=(2, _free_port(), 7), nprocs=2, join=True)
+    mp.spawn(_worker_predict, args=(3, _free_port(), 2), nprocs=3, join=True)     # one rank gets an empty shard
+
+
 def _free_port():
     s = socket.socket()
     s.bind(('127.0.0.1', 0))

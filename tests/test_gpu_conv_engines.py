@@ -125,3 +125,23 @@ def test_conv_tc_engine_split_tf32(name):
     # truncates (RZ) on every accumulate, a bias that does not average out; still 10-100x below single-pass TF32.
     assert err <= 1e-4, err
     print(f'{name}: max-rel err {err:.2e}')
+
+
+PRE_SRC2 = dict(
+    pre_concat_1x1=dict(seed=21, B=9, Tin=149, Tout=149, Cin=96, Cin2=64, N=128, pre=True, bias=True, act=1, src2_mode=2),
+    pre_add_k3=dict(seed=22, B=9, Tin=149, Tout=149, Cin=64, N=64, KT=3, padT=1, pre=True, bias=True, act=1, src2_mode=1),
+)
+
+
+@pytest.mark.parametrize('name', list(PRE_SRC2))
+def test_prologue_with_second_source_engine_ab(name):
+    """a BN-ReLU prologue combined with a second source (add / concat).  The tcgen05 gather (MODE 2) reads one
+    source, so ENGINE_AUTO must route the op to the FFMA engine (exact vs the interpreter) and an explicit ENGINE_TC
+    request must be refused loudly -- never a silently different result."""
+    from mvector import _lib as L
+    got, ref = _run_case(PRE_SRC2[name], L.ENGINE_AUTO)
+    assert np.abs(got - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+    got, ref = _run_case(PRE_SRC2[name], L.ENGINE_FFMA)
+    assert np.abs(got - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+    with pytest.raises(L.VpError):
+        _run_case(PRE_SRC2[name], L.ENGINE_TC)

@@ -25,7 +25,7 @@ def test_cabi_library_exports_every_declared_symbol():
     from mvector import _lib
     assert set(_lib.EXPORTS) == declared
     L = _lib.lib()
-    assert L.vp_abi_version() == 2
+    assert L.vp_abi_version() == 3
     assert L.vp_sizeof_op() == ctypes.sizeof(_lib.Op)
 
 
@@ -183,6 +183,35 @@ def test_host_gather_pad_native():
             assert np.array_equal(dst[i, :len(w)], w) and not dst[i, len(w):].any()
     bad = (C.c_int32 * len(ws))(*([lmax + 1] + lens[1:]))
     assert L.lib().vp_host_gather_pad(ptrs, bad, len(ws), lmax, dst.ctypes.data_as(C.c_void_p), 2) == L.VP_ERR_INVALID
+
+
+def test_host_stage_pool_reuse_slices_and_threads():
+    """vp_host_stage_h2d without a device target (gather only, no CUDA call): every slice / thread split gives the same
+    staging matrix, back-to-back jobs reuse the persistent worker pool, and a numpy-uint64 pointer table (what
+    predict_batch passes) is accepted."""
+    import ctypes as C
+    from mvector import _lib as L
+    rng = np.random.default_rng(5)
+    lens = np.asarray([int(x) for x in rng.integers(1, 3000, size=101)], dtype=np.int32)
+    ws = [rng.standard_normal(int(n)).astype(np.float32) for n in lens]
+    lmax = int(lens.max())
+    ref = np.zeros((len(ws), lmax), dtype=np.float32)
+    for i, w in enumerate(ws):
+        ref[i, :len(w)] = w
+    ptrs = np.fromiter((w.__array_interface__['data'][0] for w in ws), dtype=np.uint64, count=len(ws))
+    for rep in range(3):
+        for slice_rows, threads in ((1, 8), (7, 3), (16, 2), (101, 1), (200, 4), (5, 32)):
+            dst = np.full((len(ws), lmax), np.nan, dtype=np.float32)
+            rc = L.lib().vp_host_stage_h2d(C.c_void_p(ptrs.ctypes.data), C.c_void_p(lens.ctypes.data), len(ws), lmax,
+                                           dst.ctypes.data_as(C.c_void_p), C.c_void_p(), slice_rows, threads, C.c_void_p())
+            assert rc == 0 and np.array_equal(dst, ref), (rep, slice_rows, threads)
+    # a sub-range of the list (what a staging call of predict_batch passes): rows 40..60
+    dst = np.full((20, lmax), np.nan, dtype=np.float32)
+    rc = L.lib().vp_host_stage_h2d(C.c_void_p(ptrs.ctypes.data + 8 * 40), C.c_void_p(lens.ctypes.data + 4 * 40), 20, lmax,
+                                   dst.ctypes.data_as(C.c_void_p), C.c_void_p(), 4, 3, C.c_void_p())
+    assert rc == 0 and np.array_equal(dst, ref[40:60])
+    assert L.lib().vp_host_stage_h2d(C.c_void_p(ptrs.ctypes.data), C.c_void_p(lens.ctypes.data), len(ws), lmax,
+                                     dst.ctypes.data_as(C.c_void_p), C.c_void_p(), 0, 2, C.c_void_p()) == L.VP_ERR_INVALID
 
 
 def test_metrics_match_reference_golden():

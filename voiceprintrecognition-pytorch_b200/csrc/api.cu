@@ -19,6 +19,10 @@ struct vp_handle {
   // weights
   float* d_weights = nullptr;
   size_t weights_bytes = 0;
+  // ONE workspace arena shared by all programs of the handle (a handle runs one program at a time, stream-ordered):
+  // sized to the largest live program, so serving ragged lengths costs max(ws), not sum(ws), of device memory
+  char* d_arena = nullptr;
+  size_t arena_bytes = 0;
   // front-end
   bool fe_set = false;
   vp_frontend_desc fe{};
@@ -35,9 +39,9 @@ struct vp_program {
   vp_handle* h = nullptr;
   std::vector<vp_op> ops;
   std::vector<int> engines;   // resolved conv engine per op (VP_ENGINE_FFMA / VP_ENGINE_TC), 0 for non-conv
-  char* d_ws = nullptr;
   size_t ws_bytes = 0, in_floats = 0, out_floats = 0;
   int launches = 0;
+  int B = 0;                  // utterances (every op of a program agrees on it)
 };
 
 static int fail(vp_handle* h, int code, const char* fmt, ...) {
@@ -103,6 +107,7 @@ void vp_destroy(vp_handle* h) {
   cudaSetDevice(h->device);
   free_frontend(h);
   cudaFree(h->d_weights);
+  cudaFree(h->d_arena);
   delete h;
 }
 
@@ -187,17 +192,21 @@ size_t vp_frontend_scratch_floats(const vp_handle* h, int32_t B, int32_t Lpad) {
   return n;
 }
 
-// want_kind / want_post: -1 = whatever is configured (vp_embed_wave)
+// want_kind / want_post: -1 = whatever is configured (vp_embed_wave).
+// stage: 0 = the whole front-end; 1 = MFCC mel stage only (maximum -> ext_max[0]); 2 = MFCC clamp/DCT/CMN only, clamping
+// against the externally reduced maximum ext_max[0].
 static int run_frontend(vp_handle* h, int want_kind, int want_post, const float* wave, int B, int L, const int32_t* keep,
-                        float* feats, float* scratch, cudaStream_t st) {
+                        float* feats, float* scratch, cudaStream_t st, int stage = 0, float* ext_max = nullptr) {
   if (!h) return VP_ERR_INVALID;
   if (!h->fe_set) return fail(h, VP_ERR_INVALID, "front-end not configured (vp_frontend_set)");
   if (want_kind >= 0 && h->fe.kind != want_kind) return fail(h, VP_ERR_INVALID, "front-end kind mismatch");
   if (want_post >= 0 && h->fe.post != want_post) return fail(h, VP_ERR_INVALID, "front-end post-stage mismatch (vp_melspec vs vp_mfcc)");
-  if (!wave || !feats || !scratch || B < 1) return fail(h, VP_ERR_INVALID, "null/empty argument");
+  if ((stage != 2 && !wave) || (stage != 1 && !feats) || !scratch || B < 1) return fail(h, VP_ERR_INVALID, "null/empty argument");
+  if (stage != 0 && (h->fe.post != 1 || !ext_max)) return fail(h, VP_ERR_INVALID, "two-stage calls are for the MFCC front-end");
   const int T = vp_num_frames(h, L);
   if (T < 1) return fail(h, VP_ERR_INVALID, "waveform of %d samples is shorter than one frame (%d)", L, h->fe.win_length);
   if (h->fe.kind == 1 && L <= h->fe.n_fft / 2) return fail(h, VP_ERR_INVALID, "reflect padding needs L > n_fft/2");
+  CUDA_TRY(h, cudaSetDevice(h->device));
   FrontendParams p;
   p.wave = wave; p.feats = feats; p.partial = scratch;
   p.window = h->d_window; p.twiddle = h->d_twiddle;
@@ -214,7 +223,14 @@ static int run_frontend(vp_handle* h, int want_kind, int want_post, const float*
     m.mel = mel; m.cta_max = cta_max; m.dct = h->d_dct; m.feats = feats; m.partial = scratch;
     m.B = B; m.T = T; m.M = h->fe.n_mels; m.K = h->fe.n_out; m.fpb = FPB; m.nblk = p.nblk; m.n_max = B * p.nblk;
     m.top_db = h->fe.top_db;
-    CUDA_TRY(h, launch_frontend_mfcc(p, m, keep, st));
+    if (stage == 1) {
+      CUDA_TRY(h, launch_frontend_mfcc_mel(p, ext_max, st));
+    } else if (stage == 2) {
+      m.cta_max = ext_max; m.n_max = 1;
+      CUDA_TRY(h, launch_frontend_mfcc_finish(p, m, keep, st));
+    } else {
+      CUDA_TRY(h, launch_frontend_mfcc(p, m, keep, st));
+    }
     return VP_OK;
   }
   CUDA_TRY(h, launch_frontend(p, keep, st));
@@ -232,6 +248,14 @@ int vp_melspec(vp_handle* h, const float* wave, int32_t B, int32_t Lpad, const i
 int vp_mfcc(vp_handle* h, const float* wave, int32_t B, int32_t Lpad, const int32_t* keep, float* feats,
             float* scratch, void* stream) {
   return run_frontend(h, 1, 1, wave, B, Lpad, keep, feats, scratch, (cudaStream_t)stream);
+}
+
+int vp_mfcc_mel(vp_handle* h, const float* wave, int32_t B, int32_t Lpad, float* scratch, float* max_out, void* stream) {
+  return run_frontend(h, 1, 1, wave, B, Lpad, nullptr, nullptr, scratch, (cudaStream_t)stream, 1, max_out);
+}
+int vp_mfcc_finish(vp_handle* h, int32_t B, int32_t Lpad, const int32_t* keep, float* feats, float* scratch,
+                   const float* max_in, void* stream) {
+  return run_frontend(h, 1, 1, nullptr, B, Lpad, keep, feats, scratch, (cudaStream_t)stream, 2, const_cast<float*>(max_in));
 }
 
 int vp_weights_load(vp_handle* h, const void* blob, size_t nbytes) {
@@ -423,6 +447,9 @@ int vp_program_create(vp_handle* h, const vp_op* ops, int32_t n_ops, size_t ws_b
   p->ws_bytes = (ws_bytes + 255) & ~(size_t)255;
   p->in_floats = in_floats;
   p->out_floats = out_floats;
+  p->B = p->ops[0].B;
+  for (int i = 0; i < n_ops; ++i)
+    if (p->ops[i].src == VP_BUF_INPUT) { p->B = p->ops[i].B; break; }      // utterances of the op that reads the features
   for (int i = 0; i < n_ops; ++i) {
     int r = validate_op(p, p->ops[i], i);
     if (r != VP_OK) { delete p; return r; }
@@ -453,20 +480,34 @@ int vp_program_create(vp_handle* h, const vp_op* ops, int32_t n_ops, size_t ws_b
       p->engines[i] = VP_ENGINE_TC16;
     }
   }
-  if (cudaSetDevice(h->device) != cudaSuccess || cudaMalloc(&p->d_ws, p->ws_bytes ? p->ws_bytes : 256) != cudaSuccess) {
-    delete p;
-    return fail(h, VP_ERR_NOMEM, "workspace of %zu bytes: %s", ws_bytes, cudaGetErrorString(cudaGetLastError()));
+  if (cudaSetDevice(h->device) != cudaSuccess) { delete p; return fail(h, VP_ERR_CUDA, "cudaSetDevice"); }
+  if (p->ws_bytes > h->arena_bytes) {
+    // grow the shared arena: programs enqueued earlier may still be reading the old one -> drain the device first
+    const size_t want = p->ws_bytes + (p->ws_bytes >> 3);          // 12.5 % headroom: fewer regrows under ragged lengths
+    cudaDeviceSynchronize();
+    cudaFree(h->d_arena);
+    h->d_arena = nullptr;
+    h->arena_bytes = 0;
+    if (cudaMalloc(&h->d_arena, want) != cudaSuccess) {
+      cudaGetLastError();
+      if (cudaMalloc(&h->d_arena, p->ws_bytes) != cudaSuccess) {
+        delete p;
+        return fail(h, VP_ERR_NOMEM, "workspace of %zu bytes: %s", ws_bytes, cudaGetErrorString(cudaGetLastError()));
+      }
+      h->arena_bytes = p->ws_bytes;
+    } else {
+      h->arena_bytes = want;
+    }
   }
   *out = p;
   return VP_OK;
 }
 
 void vp_program_destroy(vp_program* p) {
-  if (!p) return;
-  cudaSetDevice(p->h->device);
-  cudaFree(p->d_ws);
-  delete p;
+  delete p;                   // host state only: the workspace is the handle's shared arena
 }
+
+size_t vp_workspace_bytes(const vp_handle* h) { return h ? h->arena_bytes : 0; }
 
 int32_t vp_program_launches(const vp_program* p) { return p ? p->launches : -1; }
 
@@ -474,7 +515,7 @@ static inline const float* rd(const vp_program* p, int64_t off, const float* in,
   if (off == VP_BUF_NONE) return nullptr;
   if (off == VP_BUF_INPUT) return in;
   if (off == VP_BUF_OUTPUT) return out;
-  return reinterpret_cast<const float*>(p->d_ws + off);
+  return reinterpret_cast<const float*>(p->h->d_arena + off);
 }
 static inline const float* wt(const vp_program* p, int64_t off) {
   return off < 0 ? nullptr : reinterpret_cast<const float*>(reinterpret_cast<const char*>(p->h->d_weights) + off);
@@ -502,6 +543,7 @@ static void fill_conv(const vp_program* p, const vp_op& o, const float* feats, f
 
 static int run_ops(vp_program* p, const float* feats, float* emb, cudaStream_t st, cudaEvent_t* evs) {
   vp_handle* h = p->h;
+  CUDA_TRY(h, cudaSetDevice(h->device));     // launch attributes / SM counts are looked up for the current device
   for (size_t i = 0; i < p->ops.size(); ++i) {
     const vp_op& o = p->ops[i];
     if (evs) CUDA_TRY(h, cudaEventRecord(evs[i], st));
@@ -612,17 +654,24 @@ int vp_program_op_info(const vp_program* p, int32_t i, int32_t* kind, int64_t* M
 int vp_embed_wave(vp_program* p, const float* wave, int32_t B, int32_t Lpad, const int32_t* keep, float* feats_scratch,
                   float* fe_scratch, float* emb, void* stream) {
   if (!p) return VP_ERR_INVALID;
+  // check the call against the program BEFORE anything is launched: the front-end writes B*T*F floats into
+  // feats_scratch, which a host sizes from the program
+  if (!p->h->fe_set) return fail(p->h, VP_ERR_INVALID, "front-end not configured (vp_frontend_set)");
+  const int T = vp_num_frames(p->h, Lpad);
+  if (B < 1 || T < 1) return fail(p->h, VP_ERR_INVALID, "empty batch / waveform shorter than one frame");
+  const size_t need = (size_t)B * T * vp_feature_dim(p->h);
+  if (need != p->in_floats)
+    return fail(p->h, VP_ERR_INVALID, "program expects %zu input floats, the front-end would produce %zu", p->in_floats, need);
+  if (B != p->B) return fail(p->h, VP_ERR_INVALID, "program was lowered for B=%d, called with B=%d", p->B, B);
   int r = run_frontend(p->h, -1, -1, wave, B, Lpad, keep, feats_scratch, fe_scratch, (cudaStream_t)stream);
   if (r != VP_OK) return r;
-  const size_t need = (size_t)B * vp_num_frames(p->h, Lpad) * vp_feature_dim(p->h);
-  if (need != p->in_floats) return fail(p->h, VP_ERR_INVALID, "program expects %zu input floats, front-end produced %zu", p->in_floats, need);
   return vp_embed(p, feats_scratch, emb, stream);
 }
 
 int vp_program_peek(vp_program* p, int64_t off, size_t nbytes, void* dst, void* stream) {
   if (!p || !dst) return VP_ERR_INVALID;
   if (off < 0 || (size_t)off + nbytes > p->ws_bytes) return fail(p->h, VP_ERR_INVALID, "peek out of range");
-  CUDA_TRY(p->h, cudaMemcpyAsync(dst, p->d_ws + off, nbytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  CUDA_TRY(p->h, cudaMemcpyAsync(dst, p->h->d_arena + off, nbytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return VP_OK;
 }
 

@@ -6,6 +6,25 @@
 
 namespace vpb {
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only: launchers remember, per device,
+// the largest dynamic shared-memory size they have opted a kernel into.
+struct PerDeviceSmem {
+  size_t cfg[64] = {};
+  // true when the kernel must be (re)configured on the current device before launching with `bytes` of dynamic smem
+  bool need(size_t bytes, int* dev_out = nullptr) {
+    int d = 0;
+    cudaGetDevice(&d);
+    if (dev_out) *dev_out = d;
+    if (d < 0 || d >= 64) return bytes > 48 * 1024;
+    return bytes > 48 * 1024 && bytes > cfg[d];
+  }
+  void set(size_t bytes) {
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d >= 0 && d < 64 && bytes > cfg[d]) cfg[d] = bytes;
+  }
+};
+
 // Resolved (device-pointer) form of a vp_op, passed to kernels by value.
 struct ConvParams {
   const float* src; const float* src2; float* dst; float* sum; const float* res; const float* gate; const float* ubias;

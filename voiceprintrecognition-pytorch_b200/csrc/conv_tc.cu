@@ -130,18 +130,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// cp.async (LDGSTS) helpers for the experimental shared-memory ring of the A producers (RING variant)
-__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-
 template <int MODE> struct Slot;
 template <> struct Slot<0> { float4 v[ROWS_PER_THREAD]; };
 template <> struct Slot<1> { float4 v[ROWS_PER_THREAD]; float4 u[ROWS_PER_THREAD]; };
@@ -175,15 +163,12 @@ struct TcArgs {
 // F16 = true (experimental, opt-in via VPB_TC_F16=1, MODE 0 only): operands are split into two fp16 terms instead of
 // two tf32 terms -- hi = fp16(x), lo = fp16(x - hi), same three MMAs, kind::f16 at twice the tf32 issue rate; a stage
 // row of 128 B then holds 64 K elements (BKE) and a producer thread moves 8 of them per row (KPT).
-// RING = true (experimental, opt-in via VPB_TC_RING=1, MODE 0 / 1, tf32 only): the producers do not stage the gathered
-// A values in registers (2-3 K blocks in flight per thread) but cp.async them into a shared-memory ring of RD raw tiles
-// and split them into hi / lo from there -- the bytes in flight are no longer bounded by the register file, which is what
-// limits the narrow-N (latency-bound) layers (profiles/r1_ncu_conv_tc.md).
-template <int MODE, bool F16 = false, bool RING = false>
+// (A cp.async shared-memory ring for the A producers was built and measured in round 2: parity-green, 5.54 vs 5.56 ms per
+// ECAPA step -- no gain, removed.  profiles/r2_staged_variants.md)
+template <int MODE, bool F16 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvParams p,
                                                                  const __grid_constant__ TcArgs a) {
   static_assert(!F16 || MODE == 0, "the fp16 split path only implements the plain / concat source mode");
-  static_assert(!RING || (!F16 && MODE != 2), "the cp.async ring implements the tf32 path for source modes 0 and 1");
   constexpr int BKE = F16 ? 64 : BK;     // K elements per pipeline stage
   constexpr int KPT = F16 ? 8 : 4;       // K elements per producer thread and row
   using SlotT = typename std::conditional<F16, SlotH, Slot<MODE>>::type;
@@ -260,94 +245,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         while (g_ci >= p.CinTot) { g_ci -= p.CinTot; if (++g_kf == p.KF) { g_kf = 0; ++g_kt; } }
     };
     cursor_reset();
-    if constexpr (RING) {
-      // ---- experimental: cp.async ring of RD raw A tiles (one commit group per K block) ----
-      constexpr int RD = (MODE == 1) ? 3 : 4;                       // raw tiles in flight
-      constexpr uint32_t RAWB = (MODE == 1) ? 2u * A_TILE : A_TILE;   // second source (MODE 1) sits behind the first
-      const uint32_t ring0 = smem_base + S * stage_bytes + EPI_PAD_BYTES;
-      const uint32_t my_off = (uint32_t)r0 * 128u + (uint32_t)chunk * 16u;     // + 32*i rows: + 4096*i bytes
-      auto issue = [&](uint32_t slot) {
-        if (g_kb == 0) {
-          const int g = cluster_id + g_tl * n_clusters;
-          const int m0 = ((g / a.n_tiles) * (int)C + (int)crank) * BM;
-#pragma unroll
-          for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-            rows[i] = decode_row(p, m0 + r0 + 32 * i);
-            if (!rows[i].valid) rows[i].t0 = -(1 << 28);
-          }
-        }
-        const int ci = g_ci;
-        const int dt = g_kt * p.dT, df = g_kf * p.dF;
-        const bool kok = g_k < p.K && !(a.debug & 2);
-        const bool second = (MODE == 0) && (p.src2_mode == VP_SRC2_CONCAT) && (ci >= p.Cin);
-        const char* base = reinterpret_cast<const char*>(second ? p.src2 + p.src2_coff + (ci - p.Cin) : p.src + p.in_coff + ci);
-        const uint32_t ldb = (uint32_t)(second ? p.src2_ld : p.in_ld) * 4u;
-        const uint32_t dst = ring0 + slot * RAWB + my_off;
-#pragma unroll
-        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-          int ti = rows[i].t0 + dt;
-          const int fi = rows[i].f0 + df;
-          if (p.pad_mode == VP_PAD_REFLECT) {
-            if (ti < 0) ti = -ti;
-            if (ti >= p.Tin) ti = 2 * (p.Tin - 1) - ti;
-          }
-          const bool ok = kok && (unsigned)ti < (unsigned)p.Tin && (unsigned)fi < (unsigned)p.Fin;
-          const uint32_t r = ok ? (uint32_t)(rows[i].base + ti * p.Fin + fi) : 0u;     // src-size 0 zero-fills; address stays valid
-          cp_async16(dst + 4096u * i, base + (uint64_t)r * ldb, ok ? 16u : 0u);
-          if constexpr (MODE == 1)
-            cp_async16(dst + A_TILE + 4096u * i,
-                       reinterpret_cast<const char*>(p.src2 + p.src2_coff + ci) + (uint64_t)r * ((uint32_t)p.src2_ld * 4u), ok ? 16u : 0u);
-        }
-        cp_async_commit();
-        if (++g_kb == a.k_blocks) {
-          ++g_tl;
-          cursor_reset();
-        } else {
-          g_k += BKE;
-          g_ci += BKE;
-          if (!pointwise)
-            while (g_ci >= p.CinTot) { g_ci -= p.CinTot; if (++g_kf == p.KF) { g_kf = 0; ++g_kt; } }
-        }
-      };
-      int p_s = 0;
-      uint32_t p_ph = 0, slot = 0;
-      for (int q = 0; q < RD && q < total_items; ++q) issue((uint32_t)q);
-      for (int q = 0; q < total_items; ++q) {
-        if (q + RD <= total_items) cp_async_wait<RD - 1>();         // item q has landed, RD - 1 younger ones may be pending
-        else cp_async_wait<0>();
-        const uint32_t src = ring0 + slot * RAWB + my_off;
-        float4 x[ROWS_PER_THREAD];
-#pragma unroll
-        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-          x[i] = lds128(src + 4096u * i);                          // this thread's own chunks: no cross-thread sync needed
-          if constexpr (MODE == 1) {
-            const float4 u = lds128(src + A_TILE + 4096u * i);
-            x[i].x += u.x; x[i].y += u.y; x[i].z += u.z; x[i].w += u.w;
-          }
-        }
-        const int s = p_s;
-        const uint32_t ph = p_ph;
-        if (++p_s == S) { p_s = 0; p_ph ^= 1u; }
-        mbar_wait(empty0 + 8 * s, ph ^ 1);
-        const uint32_t a_hi = smem_base + s * stage_bytes;
-        const uint32_t a_lo = a_hi + A_TILE;
-#pragma unroll
-        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-          const int r = r0 + 32 * i;
-          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
-          float4 hi, lo;
-          hi.x = tf32_rna(x[i].x); hi.y = tf32_rna(x[i].y); hi.z = tf32_rna(x[i].z); hi.w = tf32_rna(x[i].w);
-          lo.x = x[i].x - hi.x; lo.y = x[i].y - hi.y; lo.z = x[i].z - hi.z; lo.w = x[i].w - hi.w;
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full0 + 8 * s);
-        if (q + RD < total_items) issue(slot);                      // the slot just drained takes item q + RD
-        if (++slot == (uint32_t)RD) slot = 0;
-      }
-    } else {
+    {
       // Register prefetch slots.  gather() ONLY issues loads (no instruction may read a loaded register before publish():
       // even a predicated-off consumer stalls on the load's scoreboard and would serialise the loads); add / BN-ReLU
       // prologue are applied in publish().  MODE 0: plain or channel-concat source, 3 K blocks in flight; MODE 1: second
@@ -742,11 +640,29 @@ bool conv_tc_supported(const ConvParams& p) {
   if (p.M < 1024) return false;                       // tiny-M ops (SE / ASP bias / final FC) stay on the exact FFMA engine
   if (p.N < 16 || (p.N & 3) || (p.K & 3)) return false;
   if (p.tc_bn != tc_tile_n(p.N, p.K)) return false;
+  // the BN-ReLU prologue gather (MODE 2) reads one source only: prologue + second source stays on the FFMA engine, whose
+  // gather composes both (common.cuh::gather_a4)
+  if (p.pre_s != nullptr && p.src2_mode != VP_SRC2_NONE) return false;
   return true;
 }
 
-// f16 = true: experimental two-term FP16 split (conv_tc_kernel<0, true>); w_img is then the fp16 weight image and
-// descale the inverse of the power-of-two scale folded into it.
+// cudaFuncSetAttribute is per device: remember which devices have been configured (one Engine per device per process is
+// the norm, but nothing stops a host from creating handles on several GPUs)
+static cudaError_t configure_once(int dev) {
+  static bool done[64] = {};
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (done[dev]) return cudaSuccess;
+  const int bytes = tc::SMEM_BUDGET + tc::EPI_PAD_BYTES + 1024;
+  cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[dev] = true;
+  return e;
+}
+
+// f16 = true: two-term FP16 split (conv_tc_kernel<0, true>); w_img is then the fp16 weight image and descale the inverse
+// of the power-of-two scale folded into it.
 static cudaError_t launch_conv_tc_impl(const ConvParams& p, const float* w_img, bool f16, float descale, cudaStream_t stream) {
   using namespace tc;
   TcArgs a;
@@ -758,13 +674,6 @@ static cudaError_t launch_conv_tc_impl(const ConvParams& p, const float* w_img, 
   a.stages = SMEM_BUDGET / stage_bytes;
   if (a.stages > 8) a.stages = 8;
   if (a.stages < 2) return cudaErrorInvalidConfiguration;
-  // experimental cp.async ring (VPB_TC_RING=1): two pipeline stages + RD raw tiles must fit the same budget
-  static int ring_pref = -1;
-  if (ring_pref < 0) { const char* e = getenv("VPB_TC_RING"); ring_pref = (e && e[0] == '1') ? 1 : 0; }
-  const int mode = p.pre_s != nullptr ? 2 : (p.src2_mode == VP_SRC2_ADD ? 1 : 0);
-  const int ring_bytes = mode == 1 ? 3 * 2 * A_TILE : 4 * A_TILE;
-  const bool ring = ring_pref == 1 && !f16 && mode != 2 && 2 * stage_bytes + ring_bytes <= SMEM_BUDGET;
-  if (ring) a.stages = 2;
   a.m_tiles = (p.M + BM - 1) / BM;
   a.n_tiles = (p.N + a.BN - 1) / a.BN;
   a.k_blocks = (p.K + bke - 1) / bke;
@@ -781,32 +690,18 @@ static cudaError_t launch_conv_tc_impl(const ConvParams& p, const float* w_img, 
   static int debug_flags = -1;
   if (debug_flags < 0) { const char* e = getenv("VPB_TC_DEBUG"); debug_flags = e ? atoi(e) : 0; }
   a.debug = debug_flags;
-  const size_t smem = (size_t)a.stages * stage_bytes + EPI_PAD_BYTES + 1024 + (ring ? ring_bytes : 0);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  if (f16 || ring) {                       // the opt-in variants are configured only when they are actually selected
-    static bool configured_exp = false;
-    if (!configured_exp) {
-      cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_PAD_BYTES + 1024);
-      if (e != cudaSuccess) return e;
-      configured_exp = true;
-    }
-  }
+  const size_t smem = (size_t)a.stages * stage_bytes + EPI_PAD_BYTES + 1024;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaError_t e = configure_once(dev);
+  if (e != cudaSuccess) return e;
+  static int sm_count[64] = {};
+  if (sm_count[dev] == 0) cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+  if (sm_count[dev] > 0) sms = sm_count[dev];
   static int cluster_pref = -1;
   if (cluster_pref < 0) {
-    const char* e = getenv("VPB_TC_CLUSTER");
-    cluster_pref = e ? atoi(e) : 2;
+    const char* ev = getenv("VPB_TC_CLUSTER");
+    cluster_pref = ev ? atoi(ev) : 2;
     if (cluster_pref != 1 && cluster_pref != 2 && cluster_pref != 4) cluster_pref = 2;
   }
   int C = cluster_pref;
@@ -826,10 +721,7 @@ static cudaError_t launch_conv_tc_impl(const ConvParams& p, const float* w_img, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e;
   if (f16) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, true>, p, a);
-  else if (ring && mode == 1) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, false, true>, p, a);
-  else if (ring) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, false, true>, p, a);
   else if (p.pre_s != nullptr) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, p, a);
   else if (p.src2_mode == VP_SRC2_ADD) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, p, a);
   else e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<0>, p, a);

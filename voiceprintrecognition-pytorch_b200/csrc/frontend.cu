@@ -309,6 +309,21 @@ __global__ void __launch_bounds__(128) cmn_mask_kernel(float* feats, const float
   }
 }
 
+// out[0] = max(v[0..n)): the call-wide (or, sharded, the rank-wide) maximum of the per-CTA maxima of the MFCC mel stage
+__global__ void __launch_bounds__(256) max_reduce_kernel(const float* v, int n, float* out) {
+  __shared__ float red[8];
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += 256) m = fmaxf(m, v[i]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    m = red[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    out[0] = m;
+  }
+}
+
 size_t frontend_smem_bytes(int N, int WL, int hop, int fpb) {
   const int G = (N / 4 < 256) ? N / 4 : 256;
   const int NG = 256 / G;
@@ -321,13 +336,47 @@ size_t frontend_smem_bytes(int N, int WL, int hop, int fpb) {
 // m.feats and the CMN partial sums, then CMN + mask over the K cepstral coefficients.
 // Dynamic shared memory above 48 KB must be opted into once per kernel; remember the largest request so far.
 static cudaError_t ensure_frontend_smem(size_t smem) {
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static PerDeviceSmem once;
+  if (once.need(smem)) {
     cudaError_t e = cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
+    once.set(smem);
   }
   return cudaSuccess;
+}
+
+// MFCC stage 1 only: mel dB values + per-CTA maxima, and their maximum into max_out[0] (device) -- the scalar a sharded
+// call all-reduces (MAX) across ranks before stage 2.
+cudaError_t launch_frontend_mfcc_mel(const FrontendParams& p, float* max_out, cudaStream_t stream) {
+  size_t smem = frontend_smem_bytes(p.N, p.WL, p.hop, p.fpb);
+  cudaError_t e = ensure_frontend_smem(smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid(p.nblk, p.B);
+  frontend_kernel<<<grid, 256, smem, stream>>>(p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  max_reduce_kernel<<<1, 256, 0, stream>>>(p.cta_max, p.B * p.nblk, max_out);
+  return cudaGetLastError();
+}
+
+// MFCC stage 2 only: clamp against m.cta_max[0..n_max) (one externally reduced scalar when n_max == 1), DCT, CMN + mask.
+cudaError_t launch_frontend_mfcc_finish(const FrontendParams& p, const MfccParams& m, const int* keep, cudaStream_t stream) {
+  dim3 grid(p.nblk, p.B);
+  size_t smem2 = ((size_t)m.M * m.K + (size_t)m.fpb * (m.M + m.K) + 8) * sizeof(float);
+  static PerDeviceSmem once;
+  cudaError_t e;
+  if (once.need(smem2)) {
+    e = cudaFuncSetAttribute(mfcc_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e != cudaSuccess) return e;
+    once.set(smem2);
+  }
+  mfcc_post_kernel<<<grid, 256, smem2, stream>>>(m);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int rows = 64;
+  dim3 g2((p.T + rows - 1) / rows, p.B);
+  cmn_mask_kernel<<<g2, 128, 0, stream>>>(m.feats, m.partial, keep, p.T, m.K, p.nblk, rows);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_frontend_mfcc(const FrontendParams& p, const MfccParams& m, const int* keep, cudaStream_t stream) {
@@ -338,20 +387,7 @@ cudaError_t launch_frontend_mfcc(const FrontendParams& p, const MfccParams& m, c
   frontend_kernel<<<grid, 256, smem, stream>>>(p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  size_t smem2 = ((size_t)m.M * m.K + (size_t)m.fpb * (m.M + m.K) + 8) * sizeof(float);
-  static size_t configured2 = 0;
-  if (smem2 > 48 * 1024 && smem2 > configured2) {
-    e = cudaFuncSetAttribute(mfcc_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    if (e != cudaSuccess) return e;
-    configured2 = smem2;
-  }
-  mfcc_post_kernel<<<grid, 256, smem2, stream>>>(m);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  const int rows = 64;
-  dim3 g2((p.T + rows - 1) / rows, p.B);
-  cmn_mask_kernel<<<g2, 128, 0, stream>>>(m.feats, m.partial, keep, p.T, m.K, p.nblk, rows);
-  return cudaGetLastError();
+  return launch_frontend_mfcc_finish(p, m, keep, stream);     // clamps against all B*nblk per-CTA maxima (m.n_max)
 }
 
 cudaError_t launch_frontend(const FrontendParams& p, const int* keep, cudaStream_t stream) {

@@ -48,6 +48,8 @@ cudaError_t launch_pool2d(const PoolParams& p, cudaStream_t stream);
 
 cudaError_t launch_frontend(const FrontendParams& p, const int* keep, cudaStream_t stream);
 cudaError_t launch_frontend_mfcc(const FrontendParams& p, const MfccParams& m, const int* keep, cudaStream_t stream);
+cudaError_t launch_frontend_mfcc_mel(const FrontendParams& p, float* max_out, cudaStream_t stream);
+cudaError_t launch_frontend_mfcc_finish(const FrontendParams& p, const MfccParams& m, const int* keep, cudaStream_t stream);
 size_t frontend_smem_bytes(int N, int WL, int hop, int fpb);
 cudaError_t launch_conv_ffma(const ConvParams& p, cudaStream_t stream);
 cudaError_t launch_conv_c1(const ConvParams& p, cudaStream_t stream);

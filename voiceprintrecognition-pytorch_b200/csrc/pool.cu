@@ -79,10 +79,11 @@ __global__ void __launch_bounds__(256) colstats_kernel(const __grid_constant__ S
   }
 }
 
-// VPB_POOL_V2=1 routes the supported shapes to the experimental cp.async variants (pool_v2.cu); default: off.
+// The supported shapes run on the cp.async one-trip staging kernels (pool_v2.cu: bit-identical results, validated on B200
+// in round 2: -4.4 % per ECAPA step); VPB_POOL_V2=0 keeps the register-staged kernels below for A/B runs.
 static bool pool_v2_enabled() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("VPB_POOL_V2"); on = (e && e[0] == '1') ? 1 : 0; }
+  if (on < 0) { const char* e = getenv("VPB_POOL_V2"); on = (e && e[0] == '0') ? 0 : 1; }
   return on == 1;
 }
 
@@ -233,11 +234,11 @@ cudaError_t launch_asp_pool(const AspParams& p, cudaStream_t stream) {
   dim3 grid((p.C + 31) / 32, p.B);
   const size_t smem = (size_t)p.T * 32 * 2 * sizeof(float);
   if (smem <= 200 * 1024 && (p.C & 3) == 0 && (p.x_ld & 3) == 0 && (p.x_coff & 3) == 0 && (p.l_ld & 3) == 0 && (p.l_coff & 3) == 0) {
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static PerDeviceSmem once;
+    if (once.need(smem)) {
       cudaError_t e = cudaFuncSetAttribute(asp_pool_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       if (e != cudaSuccess) return e;
-      configured = 200 * 1024;
+      once.set(200 * 1024);
     }
     asp_pool_smem_kernel<<<grid, 256, smem, stream>>>(p);
     return cudaGetLastError();

@@ -1,4 +1,4 @@
-// EXPERIMENTAL, opt-in (VPB_POOL_V2=1), NOT yet validated on hardware -- staged for round 2.
+// One-trip cp.async staging variants of the pooling kernels (default since round 2; VPB_POOL_V2=0 disables them).
 //
 // Same contracts as asp_pool_smem_kernel / colstats_kernel (pool.cu), different data movement: the whole [rows, 32]
 // channel strip of an utterance is brought into shared memory with cp.async (LDGSTS, 16 B per request), ALL requests of
@@ -89,11 +89,11 @@ bool asp_pool_v2_supported(const AspParams& p) {
 
 cudaError_t launch_asp_pool_v2(const AspParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)p.T * 32 * 2 * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceSmem once;
+  if (once.need(100 * 1024)) {
     cudaError_t e = cudaFuncSetAttribute(asp_pool_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
-    configured = true;
+    once.set(100 * 1024);
   }
   dim3 grid((p.C + 31) / 32, p.B);
   asp_pool_v2_kernel<<<grid, 256, smem, stream>>>(p);
@@ -156,11 +156,11 @@ bool colstats_v2_supported(const StatsParams& p) {
 
 cudaError_t launch_colstats_v2(const StatsParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)p.R * 32 * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceSmem once;
+  if (once.need(100 * 1024)) {
     cudaError_t e = cudaFuncSetAttribute(colstats_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
-    configured = true;
+    once.set(100 * 1024);
   }
   dim3 grid((p.C + 31) / 32, p.B);
   colstats_v2_kernel<<<grid, 256, smem, stream>>>(p);

@@ -74,6 +74,8 @@ def lib():
         'vp_fbank': (C.c_int, [vp, f32p, i32, i32, i32p, f32p, f32p, vp]),
         'vp_melspec': (C.c_int, [vp, f32p, i32, i32, i32p, f32p, f32p, vp]),
         'vp_mfcc': (C.c_int, [vp, f32p, i32, i32, i32p, f32p, f32p, vp]),
+        'vp_mfcc_mel': (C.c_int, [vp, f32p, i32, i32, f32p, f32p, vp]),
+        'vp_mfcc_finish': (C.c_int, [vp, i32, i32, i32p, f32p, f32p, f32p, vp]),
         'vp_weights_load': (C.c_int, [vp, C.c_void_p, sz]),
         'vp_program_create': (C.c_int, [vp, C.POINTER(Op), i32, sz, sz, sz, pp]),
         'vp_program_destroy': (None, [vp]),
@@ -84,12 +86,14 @@ def lib():
         'vp_program_op_info': (C.c_int, [vp, i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
         'vp_program_peek': (C.c_int, [vp, C.c_int64, sz, C.c_void_p, vp]),
         'vp_host_gather_pad': (C.c_int, [C.c_void_p, C.c_void_p, i32, i32, C.c_void_p, i32]),
+        'vp_host_stage_h2d': (C.c_int, [C.c_void_p, C.c_void_p, i32, i32, C.c_void_p, C.c_void_p, i32, i32, vp]),
+        'vp_workspace_bytes': (sz, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if L.vp_abi_version() != 2:
+    if L.vp_abi_version() != 3:
         raise RuntimeError('libvpb200.so ABI version mismatch')
     if L.vp_sizeof_op() != C.sizeof(Op) or L.vp_sizeof_frontend_desc() != C.sizeof(FrontendDesc):
         raise RuntimeError('vp_op / vp_frontend_desc layout mismatch between the ctypes binding and libvpb200.so')
@@ -101,4 +105,5 @@ EXPORTS = ['vp_abi_version', 'vp_sizeof_op', 'vp_sizeof_frontend_desc', 'vp_crea
            'vp_frontend_set', 'vp_num_frames', 'vp_frontend_scratch_floats', 'vp_fbank', 'vp_melspec', 'vp_mfcc',
            'vp_feature_dim',
            'vp_weights_load', 'vp_program_create', 'vp_program_destroy', 'vp_embed', 'vp_embed_wave',
-           'vp_program_launches', 'vp_program_peek', 'vp_embed_profiled', 'vp_program_op_info', 'vp_host_gather_pad']
+           'vp_program_launches', 'vp_program_peek', 'vp_embed_profiled', 'vp_program_op_info', 'vp_host_gather_pad',
+           'vp_host_stage_h2d', 'vp_workspace_bytes', 'vp_mfcc_mel', 'vp_mfcc_finish']

@@ -302,8 +302,12 @@ class AudioFeaturizer:
         r = torch.as_tensor(input_lens_ratio, dtype=torch.float32).cpu()
         return torch.round(r * T).to(torch.int32)
 
-    def forward(self, waveforms, input_lens_ratio=None):
-        """waveforms [B, L] (or [L]) float32 (torch CPU/CUDA tensor or ndarray) -> CUDA tensor [B, T, F]."""
+    def forward(self, waveforms, input_lens_ratio=None, group=None):
+        """waveforms [B, L] (or [L]) float32 (torch CPU/CUDA tensor or ndarray) -> CUDA tensor [B, T, F].
+
+        ``group``: a torch.distributed process group over which ONE reference call is sharded by utterances (every rank
+        passes its shard, padded to the global longest item): only MFCC has a cross-utterance term -- the top_db clamp
+        against the maximum of the whole call -- which is then all-reduced (MAX) between the mel stage and the DCT."""
         self._ensure()
         dev = self._engine.device
         w = torch.as_tensor(waveforms)
@@ -311,23 +315,58 @@ class AudioFeaturizer:
             w = w.unsqueeze(0)
         w = w.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
         B, Lp = w.shape
-        f = self.feat_fun
-        if f.desc.kind == 0:
-            assert 2 <= f.win_length <= Lp, f'choose a window size {f.win_length} that is [2, {Lp}]'
         T = self.num_frames(Lp)
         keep = None
         if input_lens_ratio is not None:
             keep = self.keep_frames(input_lens_ratio, T).to(dev, non_blocking=True)
+        return self.forward_keep(w, keep, group=group)
+
+    def forward_keep(self, w, keep=None, group=None):
+        """Same with the mask lengths already on the device: ``w`` CUDA float32 [B, L] contiguous, ``keep`` CUDA int32 [B]
+        (frames kept per utterance, featurizer.py:82-84) or None."""
+        self._ensure()
+        dev = self._engine.device
+        B, Lp = w.shape
+        f = self.feat_fun
+        if f.desc.kind == 0:
+            assert 2 <= f.win_length <= Lp, f'choose a window size {f.win_length} that is [2, {Lp}]'
+        T = self.num_frames(Lp)
         feats = torch.empty(B, T, self.feature_dim, dtype=torch.float32, device=dev)
         lib = L.lib()
         scratch = torch.empty(max(int(lib.vp_frontend_scratch_floats(self._engine.handle, B, Lp)), 1),
                               dtype=torch.float32, device=dev)
+        kp = C.c_void_p(keep.data_ptr()) if keep is not None else C.c_void_p()
+        if group is not None and f.desc.post == 1 and f.desc.top_db >= 0:
+            self.mfcc_sharded(w, B, Lp, kp, feats, scratch, torch.cuda.current_stream(dev), group)
+            return feats
         fn = lib.vp_fbank if f.desc.kind == 0 else (lib.vp_mfcc if f.desc.post == 1 else lib.vp_melspec)
-        _check(self._engine.handle, fn(self._engine.handle, C.c_void_p(w.data_ptr()), B, Lp,
-                                       C.c_void_p(keep.data_ptr()) if keep is not None else C.c_void_p(),
+        _check(self._engine.handle, fn(self._engine.handle, C.c_void_p(w.data_ptr()), B, Lp, kp,
                                        C.c_void_p(feats.data_ptr()), C.c_void_p(scratch.data_ptr()),
                                        self._engine.stream_ptr()))
         return feats
+
+    def mfcc_sharded(self, w, B, Lp, kp, feats, scratch, stream, group):
+        """MFCC of this rank's shard of ONE sharded call: vp_mfcc_mel -> all-reduce(MAX) of the clamp maximum over
+        ``group`` -> vp_mfcc_finish, all enqueued on ``stream``.  Bit-identical to the single-process vp_mfcc of the whole
+        batch (max is exact and order independent)."""
+        import torch.distributed as dist
+        lib = L.lib()
+        h = self._engine.handle
+        mx = torch.empty(1, dtype=torch.float32, device=feats.device)
+        sp = C.c_void_p(stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            _check(h, lib.vp_mfcc_mel(h, C.c_void_p(w.data_ptr()), B, Lp, C.c_void_p(scratch.data_ptr()),
+                                      C.c_void_p(mx.data_ptr()), sp))
+            if dist.is_initialized() and dist.get_world_size(group) > 1:
+                from ..distributed import device_collectives
+                if device_collectives(group):
+                    dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+                else:                                   # gloo: one float through the host
+                    m = mx.cpu()
+                    dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+                    mx.copy_(m)
+            _check(h, lib.vp_mfcc_finish(h, B, Lp, kp, C.c_void_p(feats.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                                         C.c_void_p(mx.data_ptr()), sp))
 
     __call__ = forward
 

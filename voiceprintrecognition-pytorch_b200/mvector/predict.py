@@ -60,7 +60,7 @@ class MVectorPredictor:
         self.predictor.eval()
         self._pinned = None
         self._copy_stream = None
-        self._pool = None
+        self._ws_per_utt = {}
 
         self.speaker_diarize = SpeakerDiarization()
 
@@ -177,10 +177,25 @@ class MVectorPredictor:
             audio_segment.normalize(target_db=ds.target_dB)
         return audio_segment
 
-    #: utterances per pipeline chunk of predict_batch (host gather + H2D of chunk k+1 overlap the kernels of chunk k)
-    CHUNK = int(os.environ.get('VPB_PREDICT_CHUNK', '128'))
-    GATHER_THREADS = 4
-    COPY_SLICE = int(os.environ.get('VPB_COPY_SLICE', '128'))   # measured: slicing the H2D finer does not pay
+    #: utterances per backbone program (one fused vp_embed per chunk); the workspace limit can lower it for big 2-D nets
+    MAX_BATCH = int(os.environ.get('VPB_PREDICT_CHUNK', '256'))
+    #: utterances per staging call (host gather -> pinned -> H2D -> front-end kernels), double buffered
+    STAGE_ROWS = int(os.environ.get('VPB_STAGE_ROWS', '64'))
+    #: utterances per H2D copy inside a staging call (the copy of slice k overlaps the gather of slice k+1)
+    COPY_SLICE = int(os.environ.get('VPB_COPY_SLICE', '16'))
+    WS_LIMIT_BYTES = int(float(os.environ.get('VPB_WS_LIMIT_GB', '64')) * 2 ** 30)
+
+    @staticmethod
+    def _gather_threads():
+        """Host threads of the staging gather: what this process may use, split between the ranks of the node."""
+        if os.environ.get('VPB_GATHER_THREADS'):
+            return max(1, int(os.environ['VPB_GATHER_THREADS']))
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except AttributeError:
+            ncpu = os.cpu_count() or 1
+        local_world = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
+        return max(1, min(8, ncpu // local_world - 1))
 
     def _pinned_slot(self, slot, n):
         """Two reusable pinned host staging buffers (double buffering)."""
@@ -190,81 +205,131 @@ class MVectorPredictor:
             self._pinned[slot] = torch.empty(max(n, 1 << 20), dtype=torch.float32).pin_memory()
         return self._pinned[slot][:n]
 
-    def _embed_waves(self, waves, lmax, masked):
-        """waves: list of 1-D float32 arrays (already loaded / resampled / normalised) -> np.float32 [B, embd_dim].
+    def _chunk_size(self, B, T):
+        """Utterances per backbone program: MAX_BATCH, lowered so that the program workspace stays under WS_LIMIT_BYTES
+        (ERes2Net-55M at T = 998 needs ~0.6 GB per utterance)."""
+        cb = min(self.MAX_BATCH, B)
+        per = self._ws_per_utt.get(T)
+        if per is None:
+            per = self._ws_per_utt[T] = max(int(self.predictor.lower(1, T).peak), 1)
+        return max(1, min(cb, self.WS_LIMIT_BYTES // per))
 
-        Reference semantics (predict.py:244-262): every utterance is zero padded to the longest item of the WHOLE list,
-        T and the CMN mean follow that padded length, frames >= round(len/Lmax * T) are zeroed.  Because every op is
-        per-utterance, the list is processed in chunks of CHUNK utterances: while the GPU runs the fused
-        ``vp_embed_wave`` of chunk k, the host gathers chunk k+1 into pinned memory (a few threads; numpy releases the GIL
-        while copying) and its H2D copy runs on a second stream.  One D2H of the [B, embd] result at the end.  Measured on
-        B200 at B=256: two chunks of 128 are the best trade-off (smaller compute chunks lose more GPU efficiency than the
-        overlap buys; a single chunk exposes the whole 49 MB host gather)."""
+    def _embed_waves(self, waves, lmax, masked, to_numpy=True, group=None):
+        """waves: list of 1-D float32 arrays (already loaded / resampled / normalised) -> [B, embd_dim] (np.float32, or the
+        device tensor with ``to_numpy=False``).
+
+        Reference semantics (predict.py:244-262): every utterance is zero padded to ``lmax`` (the longest item of the WHOLE
+        batch -- the caller's batch, which under ``predict_batch_sharded`` is larger than this rank's list), T and the CMN
+        mean follow that padded length, frames >= round(len/Lmax * T) are zeroed.
+
+        Pipeline (every op is per-utterance, so slicing the batch cannot change results): staging calls of STAGE_ROWS
+        utterances -- native worker threads gather them into pinned memory and the H2D copies are issued slice by slice
+        (``vp_host_stage_h2d``) -- are double buffered against the fused front-end kernels, which run on the copy stream right
+        behind their data and write straight into the [B, T, F] feature buffer; as soon as the features of a backbone
+        chunk (<= MAX_BATCH utterances) are complete the main stream runs its program.  One D2H of the result at the end."""
         from . import _lib as L
+        import ctypes as C
         B = len(waves)
         fz = self._audio_featurizer
-        T = fz.num_frames(lmax)
-        if fz.feat_fun.desc.kind == 0:
-            assert 2 <= fz.feat_fun.win_length <= lmax, f'choose a window size {fz.feat_fun.win_length} that is [2, {lmax}]'
+        D = self.predictor.embd_dim
         dev = self.device
+        if B == 0:
+            e = torch.empty(0, D, dtype=torch.float32, device=dev)
+            return e.cpu().numpy() if to_numpy else e
+        T = fz.num_frames(lmax)
+        desc = fz.feat_fun.desc
+        if desc.kind == 0:
+            assert 2 <= fz.feat_fun.win_length <= lmax, f'choose a window size {fz.feat_fun.win_length} that is [2, {lmax}]'
+        eng = fz.engine
+        lib = L.lib()
+        F = fz.feature_dim
         keep_all = None
         if masked:
             keep_all = fz.keep_frames(torch.tensor([w.shape[0] / lmax for w in waves], dtype=torch.float32), T).to(dev)
-        eng = fz.engine
-        F = fz.feature_dim
-        D = self.predictor.embd_dim
         emb = torch.empty(B, D, dtype=torch.float32, device=dev)
-        cb = min(self.CHUNK, B)
-        if fz.feat_fun.desc.post == 1 and fz.feat_fun.desc.top_db >= 0:
-            cb = B          # MFCC's top_db clamp takes the maximum over the whole call (featurizer.py:76 on the full batch)
-        feats = torch.empty(cb * T * F, dtype=torch.float32, device=dev)
-        scratch = torch.empty(max(int(L.lib().vp_frontend_scratch_floats(eng.handle, cb, lmax)), 1), dtype=torch.float32,
-                              device=dev)
-        dwave = [torch.empty(cb * lmax, dtype=torch.float32, device=dev) for _ in range(2)]
+        feats = torch.empty(B, T * F, dtype=torch.float32, device=dev)
+        cb = self._chunk_size(B, T)
+        whole = desc.post == 1 and desc.top_db >= 0      # MFCC: the top_db clamp needs the maximum over the whole call
+        S = B if whole else min(self.STAGE_ROWS, B)
+        dwave = torch.empty(2 if B > S else 1, S * lmax, dtype=torch.float32, device=dev)
+        scratch = torch.empty(max(int(lib.vp_frontend_scratch_floats(eng.handle, S, lmax)), 1), dtype=torch.float32, device=dev)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
+        cs = self._copy_stream
+        cs_ptr = C.c_void_p(cs.cuda_stream)
         main = torch.cuda.current_stream(dev)
-        free_ev = [None, None]                       # compute finished reading device/pinned slot
-        for ci, lo in enumerate(range(0, B, cb)):
-            hi = min(lo + cb, B)
-            n = hi - lo
-            slot = ci & 1
+        cs.wait_stream(main)                            # buffers handed out by the allocator may still be in use on main
+        ptrs = np.fromiter((w.__array_interface__['data'][0] for w in waves), dtype=np.uint64, count=B)
+        lens = np.fromiter((w.shape[0] for w in waves), dtype=np.int32, count=B)
+        nthreads = self._gather_threads()
+        fe_fn = lib.vp_fbank if desc.kind == 0 else (lib.vp_mfcc if desc.post == 1 else lib.vp_melspec)
+        free_ev = [None, None]                          # front-end finished reading device slot / pinned slot reusable
+        next_chunk = 0
+        for gi, g0 in enumerate(range(0, B, S)):
+            g1 = min(g0 + S, B)
+            n = g1 - g0
+            slot = gi & 1
             if free_ev[slot] is not None:
-                free_ev[slot].synchronize()          # pinned slot may be overwritten only after its H2D + kernels
-            host = self._pinned_slot(slot, n * lmax).view(n, lmax)
-            hnp = host.numpy()
-            def fill(r0, r1, hnp=hnp, lo=lo):          # zero padding to the global longest item (predict.py:248-254)
-                for i in range(r0, r1):
-                    w = waves[lo + i]
-                    m = w.shape[0]
-                    hnp[i, :m] = w
-                    if m < lmax:
-                        hnp[i, m:] = 0.0
-            dw = dwave[slot][:n * lmax].view(n, lmax)
-            # gather in slices (a few threads; numpy releases the GIL while copying) and enqueue each slice's H2D as soon as
-            # it is staged, so the transfer of slice k overlaps the gather of slice k+1
-            sl = max(8, self.COPY_SLICE)
-            for s0 in range(0, n, sl):
-                s1 = min(s0 + sl, n)
-                if s1 - s0 >= 16 and self.GATHER_THREADS > 1:
-                    if self._pool is None:
-                        from concurrent.futures import ThreadPoolExecutor
-                        self._pool = ThreadPoolExecutor(max_workers=self.GATHER_THREADS)
-                    step = -(-(s1 - s0) // self.GATHER_THREADS)
-                    list(self._pool.map(lambda r: fill(r, min(r + step, s1)), range(s0, s1, step)))
-                else:
-                    fill(s0, s1)
-                with torch.cuda.stream(self._copy_stream):
-                    dw[s0:s1].copy_(host[s0:s1], non_blocking=True)
-            copied = torch.cuda.Event()
-            copied.record(self._copy_stream)
-            main.wait_event(copied)
-            keep = keep_all[lo:hi] if keep_all is not None else None
-            self.predictor.program(n, T).run_wave(dw, keep, feats, scratch, emb[lo:hi])
-            done = torch.cuda.Event()
-            done.record(main)
-            free_ev[slot] = done                     # slot (pinned + device) reusable once these kernels finished
-        return emb.cpu().numpy()
+                free_ev[slot].synchronize()
+            host = self._pinned_slot(slot, n * lmax)
+            dw = dwave[slot]
+            rc = lib.vp_host_stage_h2d(C.c_void_p(ptrs.ctypes.data + 8 * g0), C.c_void_p(lens.ctypes.data + 4 * g0), n, lmax,
+                                       C.c_void_p(host.data_ptr()), C.c_void_p(dw.data_ptr()), self.COPY_SLICE, nthreads, cs_ptr)
+            if rc != L.VP_OK:
+                raise L.VpError(rc, 'vp_host_stage_h2d failed')
+            kp = C.c_void_p(keep_all.data_ptr() + 4 * g0) if keep_all is not None else C.c_void_p()
+            if whole and group is not None:
+                fz.mfcc_sharded(dw, n, lmax, kp, feats, scratch, cs, group)
+            else:
+                from .engine import _check
+                _check(eng.handle, fe_fn(eng.handle, C.c_void_p(dw.data_ptr()), n, lmax, kp,
+                                         C.c_void_p(feats.data_ptr() + 4 * g0 * T * F), C.c_void_p(scratch.data_ptr()), cs_ptr))
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            free_ev[slot] = ev
+            # backbone chunks whose features are now complete
+            while next_chunk < B and min(next_chunk + cb, B) <= g1:
+                hi = min(next_chunk + cb, B)
+                main.wait_event(ev)
+                self.predictor.program(hi - next_chunk, T).run(feats[next_chunk:hi], emb[next_chunk:hi])
+                next_chunk = hi
+        # the staging / feature buffers go back to the allocator for the main stream: order the copy stream before that
+        main.wait_stream(cs)
+        return emb.cpu().numpy() if to_numpy else emb
+
+    def embed_device(self, wave_dev, lens=None, lmax=None, keep=None, group=None):
+        """Device-resident twin of ``predict_batch``'s compute half: ``wave_dev`` is a CUDA float32 ``[B, Lmax]`` matrix,
+        zero padded to the longest item of the (global) batch; ``lens`` the true sample counts (None: every row is full
+        length, i.e. no masking) or ``keep`` the precomputed device int32 mask lengths.  Returns the device tensor
+        ``[B, embd_dim]``.  One fused ``vp_embed_wave`` (front-end + backbone) per chunk of <= MAX_BATCH utterances; nothing
+        is copied or synchronised."""
+        from . import _lib as L
+        assert wave_dev.is_cuda and wave_dev.dtype == torch.float32 and wave_dev.dim() == 2 and wave_dev.is_contiguous()
+        B, Lp = wave_dev.shape
+        assert lmax is None or lmax == Lp
+        fz = self._audio_featurizer
+        T = fz.num_frames(Lp)
+        desc = fz.feat_fun.desc
+        if keep is None and lens is not None:
+            keep = fz.keep_frames(torch.tensor([n / Lp for n in lens], dtype=torch.float32), T).to(wave_dev.device)
+        D, F = self.predictor.embd_dim, fz.feature_dim
+        emb = torch.empty(B, D, dtype=torch.float32, device=wave_dev.device)
+        cb = self._chunk_size(B, T)
+        if desc.post == 1 and desc.top_db >= 0:         # MFCC: call-wide clamp -> front-end on the whole batch first
+            feats = fz.forward_keep(wave_dev, keep, group=group)
+            for lo in range(0, B, cb):
+                hi = min(lo + cb, B)
+                self.predictor.program(hi - lo, T).run(feats[lo:hi].contiguous(), emb[lo:hi])
+            return emb
+        eng = fz.engine
+        feats = torch.empty(cb * T * F, dtype=torch.float32, device=wave_dev.device)
+        scratch = torch.empty(max(int(L.lib().vp_frontend_scratch_floats(eng.handle, cb, Lp)), 1), dtype=torch.float32,
+                              device=wave_dev.device)
+        for lo in range(0, B, cb):
+            hi = min(lo + cb, B)
+            self.predictor.program(hi - lo, T).run_wave(wave_dev[lo:hi], None if keep is None else keep[lo:hi],
+                                                        feats[:(hi - lo) * T * F], scratch, emb[lo:hi])
+        return emb
 
     def predict(self, audio_data, sample_rate=16000):
         """预测一个音频的特征 (predict.py:214-229) -> np.ndarray [embd_dim]"""
