@@ -139,8 +139,10 @@ enum {                       /* VP_OP_COLSTATS modes (op.mode) */
 enum { VP_EW_GATE_RES = 0, VP_EW_AFF = 1, VP_EW_COPY = 2,
        VP_EW_PAD_COPY = 3 };  /* dst[r, 0:Cout] = (src[r, 0:Cin], zeros): any Cin / in_ld; Cout % 4 == 0 (odd feature dims) */
 enum { VP_BUF_NONE = -1, VP_BUF_INPUT = -2, VP_BUF_OUTPUT = -3 };  /* special values for activation offsets */
-enum { VP_ENGINE_AUTO = 0, VP_ENGINE_FFMA = 1, VP_ENGINE_TC = 2,   /* vp_op.engine: which conv kernel family */
-       VP_ENGINE_TC16 = 3 };   /* reported by vp_program_op_info only: TC op routed to the experimental fp16 split */
+enum { VP_ENGINE_AUTO = 0,   /* vp_op.engine: fastest eligible of the three below (TC16 > TC > FFMA) */
+       VP_ENGINE_FFMA = 1,   /* exact fp32 FFMA kernels */
+       VP_ENGINE_TC = 2,     /* tcgen05, three-pass split TF32 */
+       VP_ENGINE_TC16 = 3 }; /* tcgen05, three-pass two-term FP16 split with dynamic power-of-two activation scaling */
 
 typedef struct vp_op {
   int32_t kind;
@@ -173,13 +175,19 @@ typedef struct vp_op {
   float   eps;
   int32_t tc_bn;           /* N tile of w_tc: 256 if Cout >= 256 else Cout rounded up to 16 */
   int32_t sum_ld, sum_coff;
-  /* EXPERIMENTAL (opt-in at run time with VPB_TC_F16=1, ignored otherwise): fp16 two-term image of w for the
-   * kind::f16 variant of the tcgen05 engine.  w_tc16_q = (byte offset in the weight arena >> 4) + 1, 0 = none; layout
+  /* fp16 two-term image of w for the kind::f16 variant of the tcgen05 engine (VP_ENGINE_TC16; VPB_TC_F16=0 disables it
+   * at run time).  w_tc16_q = (byte offset in the weight arena >> 4) + 1, 0 = none; layout
    * [n_tile][k_block of 64][hi|lo][tc_bn rows][64 halves], 16-byte chunks XOR-swizzled by (row & 7); the image holds
    * w * 2^k, tc16_descale = 2^-k is applied to the accumulator. */
   int32_t w_tc16_q;
   float   tc16_descale;
-  int32_t reserved[2];
+  /* Dynamic activation range for the fp16 split: "amax slots" are uint32 words (float bits, zeroed at the start of
+   * every vp_embed) behind the program workspace.  An op with amax_out = s + 1 atomically maxes |y| over everything it
+   * writes into slot s (max is exact and order independent: results stay deterministic); a CONV with amax_in = s + 1 may
+   * run on the fp16 split and then scales its gathered activations by the power of two that puts slot s's maximum just
+   * below 2^14, so the split is range-safe whatever the magnitude of the activations.  0 = none: the op then never runs
+   * on the fp16 split (it stays on split-TF32, which has fp32's range). */
+  int32_t amax_out, amax_in;
 } vp_op;
 
 /* Upload the packed fp32 weight arena (host pointer, copied to the device; replaces any previous arena). */

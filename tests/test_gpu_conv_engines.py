@@ -40,6 +40,11 @@ def _run_case(case, engine_id):
     pb.in_floats = rows * width
     inp = View(L.BUF_INPUT, width, 0, width)
     src = inp.cols(0, Cin)
+    if engine_id == L.ENGINE_TC16:
+        # the fp16 split scales by the source tensor's tracked maximum: the source must be a workspace tensor written by
+        # a program op (here: a copy of the input columns), as it always is inside a backbone
+        src = pb.alloc(rows_in, Cin)
+        pb.ew(L.EW_COPY, inp.cols(0, Cin), src, Tin * Fin)
     src2 = None
     if src2_mode == L.SRC2_ADD:
         src2 = inp.cols(c_x2, Cin)
@@ -125,6 +130,56 @@ def test_conv_tc_engine_split_tf32(name):
     # truncates (RZ) on every accumulate, a bias that does not average out; still 10-100x below single-pass TF32.
     assert err <= 1e-4, err
     print(f'{name}: max-rel err {err:.2e}')
+
+
+TC16_CASES = ['gemm_512', 'gemm_n1536_k128', 'gemm_k1536_n128_ubias_tanh', 'stem_k5_reflect', 'tdnn_valid_k3_d3',
+              'k5_stride2_zero', 'n_tail_192', 'long_k_chunked_9216', 'long_k_chunked_4096_n128']
+
+
+@pytest.mark.parametrize('name', TC16_CASES)
+def test_conv_tc16_engine_fp16_split(name):
+    """tcgen05 two-term FP16 split (VP_ENGINE_TC16) with the dynamic power-of-two activation scale: fp32-grade."""
+    from mvector import _lib as L
+    got, ref = _run_case(CASES[name], L.ENGINE_TC16)
+    err = np.abs(got - ref).max() / max(1.0, np.abs(ref).max())
+    assert err <= 1e-4, err
+    print(f'{name}: max-rel err {err:.2e}')
+
+
+@pytest.mark.parametrize('scale', [1e-30, 1e-8, 1e-3, 1e4, 1e9, 1e30])
+def test_conv_tc16_is_range_safe(scale):
+    """Un-normalised activations: the fp16 split must neither overflow (|x| > 65504) nor lose small tensors to fp16
+    subnormals -- the scale comes from the tensor's tracked maximum, so the relative error does not depend on magnitude."""
+    from mvector import _lib as L
+    case = dict(CASES['gemm_512'], post=False, bias=False, act=0, scale=scale, seed=31)
+    got, ref = _run_case(case, L.ENGINE_TC16)
+    assert np.isfinite(got).all()
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err <= 2e-5, (scale, err)
+
+
+def test_conv_tc16_refused_without_tracked_source():
+    """A CONV reading the raw program input has no amax slot: an explicit TC16 request is refused, AUTO picks split TF32."""
+    from mvector import _lib as L
+    from mvector.engine import Engine, PlanBuilder, Program, View, WeightArena
+    rng = np.random.default_rng(0)
+    arena = WeightArena()
+    w = arena.add_conv('w', rng.standard_normal((256, 256)) / 16)
+    for pref, expect in ((L.ENGINE_TC16, None), (L.ENGINE_AUTO, L.ENGINE_TC)):
+        pb = PlanBuilder(8, pref)
+        pb.in_floats = 8 * 200 * 256
+        pb.conv(View(L.BUF_INPUT, 256, 0, 256), pb.output_view(256, 8 * 200), w, 256, 200, 200)
+        eng = Engine()
+        eng.load_weights(arena.blob())
+        if expect is None:
+            with pytest.raises(L.VpError):
+                Program(eng, pb)
+        else:
+            prog = Program(eng, pb)
+            y = torch.empty(8 * 200, 256, device='cuda')
+            ops = prog.run_profiled(torch.randn(8 * 200 * 256, device='cuda'), y)
+            assert ops[0]['engine'] == expect
+        eng.close()
 
 
 PRE_SRC2 = dict(

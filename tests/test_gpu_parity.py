@@ -582,11 +582,10 @@ np.savez(sys.argv[1], **out)
         assert np.array_equal(res['0'][k], res['1'][k]), k
 
 
-@pytest.mark.skipif(os.environ.get('VPB_TEST_EXPERIMENTAL') != '1',
-                    reason='opt-in: experimental two-term FP16 split of the tcgen05 engine, staged for round 2')
-def test_experimental_tc_f16_split_parity():
-    """VPB_TC_F16=1 routes the wide pointwise / conv layers to conv_tc_kernel<0, true> (kind::f16, hi/lo fp16 terms).
-    Gate: the same 1e-4 embedding parity against the oracle, and the fp16 engine must actually have run."""
+def test_tc_f16_split_runs_and_tf32_fallback_agrees():
+    """ENGINE_AUTO routes the wide pointwise / conv layers to conv_tc_kernel<0, true> (kind::f16, hi/lo fp16 terms, dynamic
+    activation scale).  Gate: the same 1e-4 embedding parity against the oracle, and the fp16 engine must actually have
+    run; with VPB_TC_F16=0 the same models stay on split TF32 and pass the same gate."""
     import subprocess
     import sys
     code = r'''
@@ -619,6 +618,11 @@ print('TC_F16_OK')
     env = dict(os.environ, VPB_TC_F16='1')
     r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=900,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and 'TC_F16_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+    off = code.replace("assert any(o['engine'] == L.ENGINE_TC16 for o in ops), name + ': fp16 engine not selected'",
+                       "assert not any(o['engine'] == L.ENGINE_TC16 for o in ops), name + ': fp16 engine ran with VPB_TC_F16=0'")
+    r = subprocess.run([sys.executable, '-c', off], env=dict(os.environ, VPB_TC_F16='0'), capture_output=True, text=True,
+                       timeout=900, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0 and 'TC_F16_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 

@@ -22,6 +22,7 @@ def export(model, B, T, path):
     from mvector import _lib as L
     pb = model.lower(B, T)
     blob = np.ascontiguousarray(model._blob, dtype=np.float32)
+    pb.finalize()
     ops = (L.Op * len(pb.ops))(*pb.ops)
     with open(path, 'wb') as f:
         f.write(MAGIC)

@@ -42,6 +42,9 @@ struct vp_program {
   size_t ws_bytes = 0, in_floats = 0, out_floats = 0;
   int launches = 0;
   int B = 0;                  // utterances (every op of a program agrees on it)
+  int n_slots = 0;            // amax slots (uint32 each) behind the workspace, zeroed at the start of every run
+  size_t arena_need() const { return ws_bytes + (((size_t)n_slots * 4 + 255) & ~(size_t)255); }
+  unsigned* slot(int32_t q) const { return q > 0 ? reinterpret_cast<unsigned*>(h->d_arena + ws_bytes) + (q - 1) : nullptr; }
 };
 
 static int fail(vp_handle* h, int code, const char* fmt, ...) {
@@ -61,10 +64,11 @@ static int fail(vp_handle* h, int code, const char* fmt, ...) {
 
 static const int FPB = 16;   // frames per front-end CTA
 
-// VPB_TC_F16=1 routes eligible tensor-core convs to the experimental two-term FP16 split (conv_tc.cu); default: off.
+// VP_ENGINE_AUTO prefers the two-term FP16 split of the tcgen05 engine where an op is eligible (conv_tc16_supported);
+// VPB_TC_F16=0 keeps AUTO on split TF32 (A/B runs).
 static bool tc16_enabled() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("VPB_TC_F16"); on = (e && e[0] == '1') ? 1 : 0; }
+  if (on < 0) { const char* e = getenv("VPB_TC_F16"); on = (e && e[0] == '0') ? 0 : 1; }
   return on == 1;
 }
 
@@ -306,6 +310,10 @@ static int check_w(vp_program* p, const char* what, int64_t off, size_t floats, 
 static int validate_op(vp_program* p, const vp_op& o, int i) {
   vp_handle* h = p->h;
   if (o.B < 1) return fail(h, VP_ERR_INVALID, "op %d: B", i);
+  if (o.amax_out < 0 || o.amax_out > 65536 || o.amax_in < 0 || o.amax_in > 65536) return fail(h, VP_ERR_INVALID, "op %d: amax slot", i);
+  if (o.amax_in > 0 && o.kind != VP_OP_CONV) return fail(h, VP_ERR_INVALID, "op %d: amax_in is a CONV field", i);
+  if (o.amax_out > 0 && (o.kind == VP_OP_COLSTATS || o.kind == VP_OP_ASP_POOL))
+    return fail(h, VP_ERR_UNSUPPORTED, "op %d: pooling ops do not track amax", i);
   switch (o.kind) {
     case VP_OP_CONV:
     case VP_OP_CONV_C1: {
@@ -458,43 +466,51 @@ int vp_program_create(vp_handle* h, const vp_op* ops, int32_t n_ops, size_t ws_b
   p->engines.assign(n_ops, 0);
   for (int i = 0; i < n_ops; ++i) {
     const vp_op& o = p->ops[i];
+    if (o.amax_out > p->n_slots) p->n_slots = o.amax_out;
+    if (o.amax_in > p->n_slots) p->n_slots = o.amax_in;
+  }
+  if (p->n_slots > 0) ++p->launches;             // the memset node that zeroes the slots
+  for (int i = 0; i < n_ops; ++i) {
+    const vp_op& o = p->ops[i];
     if (o.kind != VP_OP_CONV) continue;
     ConvParams c;
     fill_conv(p, o, nullptr, nullptr, c);
+    c.amax_in = o.amax_in > 0 ? reinterpret_cast<const unsigned*>(8) : nullptr;     // eligibility only (not dereferenced)
     const bool ok = conv_tc_supported(c);
-    if (o.engine == VP_ENGINE_TC && !ok) {
-      int r = fail(h, VP_ERR_UNSUPPORTED, "op %d: shape not supported by the tcgen05 engine", i);
-      delete p;
-      return r;
-    }
-    p->engines[i] = (o.engine == VP_ENGINE_TC || (o.engine == VP_ENGINE_AUTO && ok)) ? VP_ENGINE_TC : VP_ENGINE_FFMA;
-    // experimental fp16 split: only with VPB_TC_F16=1, only for internal (normalised) activations, never the raw input
-    if (p->engines[i] == VP_ENGINE_TC && tc16_enabled() && o.w_tc16_q > 0 && o.src != VP_BUF_INPUT && conv_tc16_supported(c)) {
+    bool ok16 = ok && o.w_tc16_q > 0 && o.tc16_descale > 0.f && conv_tc16_supported(c);
+    if (ok16) {
       const int bn = o.tc_bn, nt = (o.Cout + bn - 1) / bn, kb = (c.K + 63) / 64;
       const size_t off = (size_t)(o.w_tc16_q - 1) << 4, bytes = (size_t)nt * kb * 2 * bn * 128;
-      if (off + bytes > h->weights_bytes || !(o.tc16_descale > 0.f)) {
+      if (off + bytes > h->weights_bytes) {
         int r = fail(h, VP_ERR_INVALID, "op %d: fp16 weight image out of range", i);
         delete p;
         return r;
       }
-      p->engines[i] = VP_ENGINE_TC16;
     }
+    if ((o.engine == VP_ENGINE_TC && !ok) || (o.engine == VP_ENGINE_TC16 && !ok16)) {
+      int r = fail(h, VP_ERR_UNSUPPORTED, "op %d: shape / operands not supported by the requested tcgen05 engine", i);
+      delete p;
+      return r;
+    }
+    if (o.engine == VP_ENGINE_TC16 || (o.engine == VP_ENGINE_AUTO && ok16 && tc16_enabled())) p->engines[i] = VP_ENGINE_TC16;
+    else if (o.engine == VP_ENGINE_TC || (o.engine == VP_ENGINE_AUTO && ok)) p->engines[i] = VP_ENGINE_TC;
+    else p->engines[i] = VP_ENGINE_FFMA;
   }
   if (cudaSetDevice(h->device) != cudaSuccess) { delete p; return fail(h, VP_ERR_CUDA, "cudaSetDevice"); }
-  if (p->ws_bytes > h->arena_bytes) {
+  if (p->arena_need() > h->arena_bytes) {
     // grow the shared arena: programs enqueued earlier may still be reading the old one -> drain the device first
-    const size_t want = p->ws_bytes + (p->ws_bytes >> 3);          // 12.5 % headroom: fewer regrows under ragged lengths
+    const size_t want = p->arena_need() + (p->arena_need() >> 3);  // 12.5 % headroom: fewer regrows under ragged lengths
     cudaDeviceSynchronize();
     cudaFree(h->d_arena);
     h->d_arena = nullptr;
     h->arena_bytes = 0;
     if (cudaMalloc(&h->d_arena, want) != cudaSuccess) {
       cudaGetLastError();
-      if (cudaMalloc(&h->d_arena, p->ws_bytes) != cudaSuccess) {
+      if (cudaMalloc(&h->d_arena, p->arena_need()) != cudaSuccess) {
         delete p;
         return fail(h, VP_ERR_NOMEM, "workspace of %zu bytes: %s", ws_bytes, cudaGetErrorString(cudaGetLastError()));
       }
-      h->arena_bytes = p->ws_bytes;
+      h->arena_bytes = p->arena_need();
     } else {
       h->arena_bytes = want;
     }
@@ -539,11 +555,14 @@ static void fill_conv(const vp_program* p, const vp_op& o, const float* feats, f
   c.pad_mode = o.pad_mode; c.w_ld = o.w_ld; c.pre_relu = o.pre_relu; c.act = o.act; c.act2 = o.act2;
   c.seg_len = o.seg_len; c.n_seg = o.n_seg;
   c.M = o.B * o.Tout * o.Fout; c.N = o.Cout; c.K = o.KT * o.KF * c.CinTot;
+  c.amax_out = p->h->d_arena ? p->slot(o.amax_out) : nullptr;
+  c.amax_in = p->h->d_arena ? p->slot(o.amax_in) : nullptr;
 }
 
 static int run_ops(vp_program* p, const float* feats, float* emb, cudaStream_t st, cudaEvent_t* evs) {
   vp_handle* h = p->h;
   CUDA_TRY(h, cudaSetDevice(h->device));     // launch attributes / SM counts are looked up for the current device
+  if (p->n_slots > 0) CUDA_TRY(h, cudaMemsetAsync(h->d_arena + p->ws_bytes, 0, (size_t)p->n_slots * 4, st));
   for (size_t i = 0; i < p->ops.size(); ++i) {
     const vp_op& o = p->ops[i];
     if (evs) CUDA_TRY(h, cudaEventRecord(evs[i], st));
@@ -587,6 +606,7 @@ static int run_ops(vp_program* p, const float* feats, float* emb, cudaStream_t s
         q.B = o.B; q.Tin = o.Tin; q.Fin = o.Fin; q.Tout = o.Tout; q.Fout = o.Fout; q.C = o.Cin;
         q.in_ld = o.in_ld; q.in_coff = o.in_coff; q.out_ld = o.out_ld; q.out_coff = o.out_coff;
         q.KT = o.KT; q.KF = o.KF; q.sT = o.sT; q.sF = o.sF; q.padT = o.padT; q.padF = o.padF; q.mode = o.mode;
+        q.amax_out = p->slot(o.amax_out);
         CUDA_TRY(h, launch_pool2d(q, st));
         break;
       }
@@ -602,6 +622,7 @@ static int run_ops(vp_program* p, const float* feats, float* emb, cudaStream_t s
         e.x_ld = o.in_ld; e.x_coff = o.in_coff; e.y_ld = o.src2_ld; e.y_coff = o.src2_coff;
         e.att_ld = o.res_ld; e.att_coff = o.res_coff; e.res_ld = o.res_ld; e.res_coff = o.res_coff;
         e.out_ld = o.out_ld; e.out_coff = o.out_coff; e.mode = o.mode; e.act2 = o.act2; e.C_out = o.Cout;
+        e.amax_out = p->slot(o.amax_out);
         CUDA_TRY(h, launch_ew(e, st));
         break;
       }

@@ -35,6 +35,8 @@ struct ConvParams {
   int Tout, Fout, out_ld, out_coff, res_ld, res_coff;
   int KT, KF, sT, sF, dT, dF, padT, padF, pad_mode;
   int w_ld, pre_relu, act, act2, seg_len, n_seg, tc_bn, sum_ld, sum_coff;
+  unsigned* amax_out;                // slot this op maxes |y| into (or null)
+  const unsigned* amax_in;           // slot holding max |x| of the source tensor (fp16 split only, else null)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -58,6 +60,25 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+
+// ---- amax slots (dynamic activation range of the fp16 split; include/vpb200.h vp_op.amax_out / amax_in) ----
+// |v| as float bits order like unsigned integers, so one atomicMax per warp keeps the running maximum; max is exact and
+// order independent, hence deterministic.
+__device__ __forceinline__ float amax4(float m, const float4& v) {
+  return fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fabsf(v.y), fmaxf(fabsf(v.z), fabsf(v.w))));
+}
+__device__ __forceinline__ void amax_commit(unsigned* slot, float m) {     // whole warp must call
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
+}
+// exponent s such that amax * 2^s lies in [2^13, 2^14): fp16 hi terms stay below 65504, lo terms above the subnormals
+__device__ __forceinline__ int f16_scale_exp(unsigned amax_bits) {
+  const int be = (int)((amax_bits >> 23) & 0xffu);
+  if (amax_bits == 0u || be == 0xff) return 0;          // all-zero tensor, or inf / nan (propagates like the reference)
+  int s = 13 - (be - 127);
+  return s < -100 ? -100 : (s > 100 ? 100 : s);
+}
+__device__ __forceinline__ float exp2i(int s) { return __uint_as_float((unsigned)(s + 127) << 23); }
 
 // Decoded A-operand row (one output position): where its receptive field starts in the source map.
 struct RowInfo {

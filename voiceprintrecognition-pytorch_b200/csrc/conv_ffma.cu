@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(256, 2) conv_ffma_kernel(const __grid_constant
   }
 
   // ---- fused epilogue ----
+  float tmax = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(256, 2) conv_ffma_kernel(const __grid_constant
           o.w = epilogue1(p, acc[i][h * 4 + 3], m, n + 3, urow);
           *reinterpret_cast<float4*>(orow + n) = o;
           sum_add4(p, m, n, o);
+          tmax = amax4(tmax, o);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(256, 2) conv_ffma_kernel(const __grid_constant
               const float y = epilogue1(p, acc[i][h * 4 + j], m, n + j, urow);
               orow[n + j] = y;
               sum_add1(p, m, n + j, y);
+              tmax = fmaxf(tmax, fabsf(y));
             }
         }
       }
@@ -144,9 +147,11 @@ __global__ void __launch_bounds__(256, 2) conv_ffma_kernel(const __grid_constant
           const float y = epilogue1(p, acc[i][j], m, n + j, urow);
           orow[n + j] = y;
           sum_add1(p, m, n + j, y);
+          tmax = fmaxf(tmax, fabsf(y));
         }
     }
   }
+  if (p.amax_out) amax_commit(p.amax_out, tmax);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -197,11 +202,14 @@ __global__ void __launch_bounds__(256) linear_small_m_kernel(const __grid_consta
     if (lane == j) mine = t;
   }
   const int n = n0 + lane;
+  float tmax = 0.f;
   if (mok && n < p.N) {
     const float y = epilogue1(p, mine, m, n, urow_of(p, m));
     p.dst[(size_t)m * p.out_ld + p.out_coff + n] = y;
     sum_add1(p, m, n, y);
+    tmax = fabsf(y);
   }
+  if (p.amax_out) amax_commit(p.amax_out, tmax);
 }
 
 static bool small_m_ok(const ConvParams& p) {
@@ -240,6 +248,7 @@ __global__ void __launch_bounds__(256) conv_c1_kernel(const __grid_constant__ Co
   const int groups = p.N >> 2;
   const long long total = (long long)p.M * groups;
   const int taps = p.KT * p.KF;
+  float tmax = 0.f;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(idx % groups);
@@ -264,10 +273,12 @@ __global__ void __launch_bounds__(256) conv_c1_kernel(const __grid_constant__ Co
     (void)taps;
     const int urow = urow_of(p, m);
     const int n = g * 4;
-    *reinterpret_cast<float4*>(p.dst + (size_t)m * p.out_ld + p.out_coff + n) =
-        make_float4(epilogue1(p, a0, m, n, urow), epilogue1(p, a1, m, n + 1, urow), epilogue1(p, a2, m, n + 2, urow),
-                    epilogue1(p, a3, m, n + 3, urow));
+    const float4 o = make_float4(epilogue1(p, a0, m, n, urow), epilogue1(p, a1, m, n + 1, urow), epilogue1(p, a2, m, n + 2, urow),
+                                 epilogue1(p, a3, m, n + 3, urow));
+    *reinterpret_cast<float4*>(p.dst + (size_t)m * p.out_ld + p.out_coff + n) = o;
+    tmax = amax4(tmax, o);
   }
+  if (p.amax_out) amax_commit(p.amax_out, tmax);
 }
 
 cudaError_t launch_conv_c1(const ConvParams& p, cudaStream_t stream) {

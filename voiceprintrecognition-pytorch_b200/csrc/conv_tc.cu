@@ -314,6 +314,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       constexpr int DEPTH = (MODE == 0 && !F16) ? 3 : 2;
       int p_s = 0;
       uint32_t p_ph = 0;
+      // fp16 split: dynamic power-of-two activation scale from the source tensor's amax slot (written by the ops that
+      // produced the tensor, complete at kernel start) -> |x * ascale| < 2^14, range-safe for any activation magnitude
+      float ascale = 1.f;
+      if constexpr (F16) ascale = exp2i(f16_scale_exp(__ldg(p.amax_in)));
       auto publish = [&](int q, SlotT& sl) {
         const int s = p_s;
         const uint32_t ph = p_ph;
@@ -327,7 +331,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
           if constexpr (F16) {
             // 8 consecutive K elements -> one 16-byte chunk of fp16 hi and one of fp16 lo (lo = x - hi, exact in fp32)
-            const float xs[8] = {sl.v[i].x, sl.v[i].y, sl.v[i].z, sl.v[i].w, sl.w[i].x, sl.w[i].y, sl.w[i].z, sl.w[i].w};
+            const float xs[8] = {sl.v[i].x * ascale, sl.v[i].y * ascale, sl.v[i].z * ascale, sl.v[i].w * ascale,
+                                 sl.w[i].x * ascale, sl.w[i].y * ascale, sl.w[i].z * ascale, sl.w[i].w * ascale};
             uint32_t hw[4], lw[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -466,6 +471,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     uint32_t ccount = 0;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const uint32_t run_col = (uint32_t)(2 * BN);   // running-sum accumulator (only when n_chunks > 1)
+    float descale = 1.f;                           // fp16 split: 2^-k of the weight image x 2^-s of the activation scale
+    if constexpr (F16) descale = a.descale * exp2i(-f16_scale_exp(__ldg(p.amax_in)));
+    float tmax = 0.f;                              // running max |y| of everything this thread stores (amax_out slot)
     for (int g = cluster_id; g < total_groups; g += n_clusters) {
       const int mbase = ((g / a.n_tiles) * (int)C + (int)crank) * BM + warp * 32;
       const int n0 = (g % a.n_tiles) * BN;
@@ -541,7 +549,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             v[i] = *reinterpret_cast<const float4*>(pad + (rsub + 4 * i) * 36 + cg);
-            if constexpr (F16) { v[i].x *= a.descale; v[i].y *= a.descale; v[i].z *= a.descale; v[i].w *= a.descale; }
+            if constexpr (F16) { v[i].x *= descale; v[i].y *= descale; v[i].z *= descale; v[i].w *= descale; }
             v[i].x += b4.x; v[i].y += b4.y; v[i].z += b4.z; v[i].w += b4.w;
           }
           if (p.ubias) {
@@ -590,7 +598,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            if (rowok & (1u << i)) *reinterpret_cast<float4*>(optr[i] + c0) = v[i];
+            if (rowok & (1u << i)) {
+              *reinterpret_cast<float4*>(optr[i] + c0) = v[i];
+              tmax = amax4(tmax, v[i]);
+            }
           if (p.sum) {                         // accumulate-into view (Res2 chains): sum[m, n] += y[m, n]
             // all eight loads first, then the adds and stores: written as load-add-store per row the possible aliasing
             // between rows forces the compiler to serialise eight global round trips per chunk
@@ -612,6 +623,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         __syncwarp();
       }
     }
+    if (p.amax_out) amax_commit(p.amax_out, tmax);     // one atomicMax per epilogue warp per launch
   }
 
   tc_fence_before();
@@ -733,11 +745,11 @@ cudaError_t launch_conv_tc(const ConvParams& p, cudaStream_t stream) {
   return launch_conv_tc_impl(p, p.w_tc, false, 1.f, stream);
 }
 
-// Experimental FP16-split engine (opt-in, see api.cu): plain / concat source only, 8-element channel granularity, and
-// the same tiling rule as the tf32 image.  The activations are split unscaled (fp16 range: |x| < 65504), so the caller
-// must not route the raw program input (un-normalised features) through it.
+// FP16-split engine: plain / concat source only, 8-element channel granularity, the same tiling rule as the tf32 image,
+// and a source tensor whose amax slot is tracked (dynamic power-of-two activation scale -> range-safe).
 bool conv_tc16_supported(const ConvParams& p) {
   if (!conv_tc_supported(p)) return false;
+  if (p.amax_in == nullptr) return false;
   if (p.pre_s != nullptr || p.src2_mode == VP_SRC2_ADD) return false;
   if ((p.Cin & 7) || (p.CinTot & 7) || (p.K & 7)) return false;
   return p.N >= 128;                                  // narrow layers are not tensor bound: nothing to gain

@@ -38,11 +38,13 @@ struct EwParams {
   long long rows; int C, rows_per_utt;
   int x_ld, x_coff, y_ld, y_coff, att_ld, att_coff, res_ld, res_coff, out_ld, out_coff, mode, act2;
   int C_out;   // PAD_COPY: destination width (>= C, zero filled)
+  unsigned* amax_out;
 };
 
 struct PoolParams {
   const float* src; float* dst;
   int B, Tin, Fin, Tout, Fout, C, in_ld, in_coff, out_ld, out_coff, KT, KF, sT, sF, padT, padF, mode;
+  unsigned* amax_out;
 };
 cudaError_t launch_pool2d(const PoolParams& p, cudaStream_t stream);
 
@@ -59,7 +61,7 @@ cudaError_t launch_ew(const EwParams& p, cudaStream_t stream);
 // tcgen05 engine (conv_tc.cu)
 bool conv_tc_supported(const ConvParams& p);
 cudaError_t launch_conv_tc(const ConvParams& p, cudaStream_t stream);
-// experimental two-term FP16 split (opt-in, VPB_TC_F16=1)
+// two-term FP16 split of the same engine (VP_ENGINE_TC16)
 bool conv_tc16_supported(const ConvParams& p);
 cudaError_t launch_conv_tc16(const ConvParams& p, const float* w_tc16, float descale, cudaStream_t stream);
 

@@ -251,6 +251,7 @@ cudaError_t launch_asp_pool(const AspParams& p, cudaStream_t stream) {
 __global__ void __launch_bounds__(256) ew_kernel(const __grid_constant__ EwParams p) {
   const int c4n = p.C >> 2;
   const long long total = p.rows * c4n;
+  float tmax = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long m = i / c4n;
     const int c = (int)(i - m * c4n) * 4;
@@ -276,17 +277,23 @@ __global__ void __launch_bounds__(256) ew_kernel(const __grid_constant__ EwParam
       v.w = v.w * aw + y.w * (2.f - aw);
     }
     *reinterpret_cast<float4*>(p.dst + m * p.out_ld + p.out_coff + c) = v;
+    tmax = amax4(tmax, v);
   }
+  if (p.amax_out) amax_commit(p.amax_out, tmax);
 }
 
 // dst[r, 0:C_out] = (x[r, 0:C], 0 ...): scalar, for feature dims that are not multiples of 4 (Spectrogram's n_fft/2+1 bins)
 __global__ void __launch_bounds__(256) pad_copy_kernel(const __grid_constant__ EwParams p) {
   const long long total = p.rows * p.C_out;
+  float tmax = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long m = i / p.C_out;
     const int c = (int)(i - m * p.C_out);
-    p.dst[m * p.out_ld + p.out_coff + c] = c < p.C ? __ldg(p.x + m * p.x_ld + p.x_coff + c) : 0.f;
+    const float v = c < p.C ? __ldg(p.x + m * p.x_ld + p.x_coff + c) : 0.f;
+    p.dst[m * p.out_ld + p.out_coff + c] = v;
+    tmax = fmaxf(tmax, fabsf(v));
   }
+  if (p.amax_out) amax_commit(p.amax_out, tmax);
 }
 
 cudaError_t launch_ew(const EwParams& p, cudaStream_t stream) {
@@ -310,6 +317,7 @@ cudaError_t launch_ew(const EwParams& p, cudaStream_t stream) {
 __global__ void __launch_bounds__(256) pool2d_kernel(const __grid_constant__ PoolParams p) {
   const int c4n = p.C >> 2;
   const long long total = (long long)p.B * p.Tout * p.Fout * c4n;
+  float tmax = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4n) * 4;
     long long m = i / c4n;
@@ -334,7 +342,9 @@ __global__ void __launch_bounds__(256) pool2d_kernel(const __grid_constant__ Poo
       acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
     }
     *reinterpret_cast<float4*>(p.dst + ((size_t)(b * p.Tout + to) * p.Fout + fo) * p.out_ld + p.out_coff + c) = acc;
+    tmax = amax4(tmax, acc);
   }
+  if (p.amax_out) amax_commit(p.amax_out, tmax);
 }
 
 cudaError_t launch_pool2d(const PoolParams& p, cudaStream_t stream) {

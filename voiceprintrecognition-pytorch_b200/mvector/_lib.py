@@ -37,7 +37,7 @@ class Op(C.Structure):
                                             'KT', 'KF', 'sT', 'sF', 'dT', 'dF', 'padT', 'padF', 'pad_mode',
                                             'w_ld', 'pre_relu', 'act', 'act2', 'seg_len', 'n_seg')]
                 + [('eps', C.c_float), ('tc_bn', C.c_int32), ('sum_ld', C.c_int32), ('sum_coff', C.c_int32),
-                   ('w_tc16_q', C.c_int32), ('tc16_descale', C.c_float), ('reserved', C.c_int32 * 2)])
+                   ('w_tc16_q', C.c_int32), ('tc16_descale', C.c_float), ('amax_out', C.c_int32), ('amax_in', C.c_int32)])
 
 
 class VpError(RuntimeError):

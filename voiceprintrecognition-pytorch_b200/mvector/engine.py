@@ -14,7 +14,7 @@ import torch
 from . import _lib as L
 
 ALIGN = 256  # bytes; every workspace buffer / weight tensor starts on a 256 B boundary
-TC_F16 = os.environ.get('VPB_TC_F16', '0') == '1'   # experimental fp16 split engine (conv_tc.cu); default off
+TC_F16 = os.environ.get('VPB_TC_F16', '1') != '0'   # pack the fp16 two-term weight images (VP_ENGINE_TC16); VPB_TC_F16=0: tf32 only
 
 
 def _check(handle, rc):
@@ -89,7 +89,7 @@ class WeightArena:
             img, bn = pack_tc(W2d)
             d['w_tc'] = self.add(name + '.tc', img)
             d['tc_bn'] = bn
-            if TC_F16 and W2d.shape[0] >= 128 and W2d.shape[1] >= 8 and W2d.shape[1] % 8 == 0:      # experimental fp16 split image (opt-in)
+            if TC_F16 and W2d.shape[0] >= 128 and W2d.shape[1] >= 8 and W2d.shape[1] % 8 == 0:      # fp16 two-term image (VP_ENGINE_TC16)
                 img16, descale = pack_tc16(W2d, bn)
                 d['w_tc16'] = self.add(name + '.tc16', img16)
                 d['tc16_descale'] = descale
@@ -170,15 +170,17 @@ def unpack_tc16(img, N, K, bn):
 
 
 class View:
-    """A [rows, C] window into an activation buffer: byte offset, row stride (floats), first column, columns."""
-    __slots__ = ('off', 'ld', 'coff', 'C')
+    """A [rows, C] window into an activation buffer: byte offset, row stride (floats), first column, columns.  ``aid`` is
+    the planner's allocation id (None for the program input / output and hand-made views): ops that touch the same
+    allocation are linked through it when the amax slots of the fp16 split are assigned (PlanBuilder.finalize)."""
+    __slots__ = ('off', 'ld', 'coff', 'C', 'aid')
 
-    def __init__(self, off, ld, coff, C_):
-        self.off, self.ld, self.coff, self.C = off, ld, coff, C_
+    def __init__(self, off, ld, coff, C_, aid=None):
+        self.off, self.ld, self.coff, self.C, self.aid = off, ld, coff, C_, aid
 
     def cols(self, start, n):
         assert 0 <= start and start + n <= self.C
-        return View(self.off, self.ld, self.coff + start, n)
+        return View(self.off, self.ld, self.coff + start, n, self.aid)
 
 
 
@@ -197,6 +199,9 @@ class PlanBuilder:
         self.in_floats = 0
         self.out_floats = 0
         self.taps = OrderedDict()   # name -> (View, rows) for tests (vp_program_peek)
+        self._next_aid = 0
+        self._meta = []             # per op: allocation ids of (dst, src, src2, sum) -- see finalize()
+        self._finalized = False
 
     # ---- memory ----
     def alloc(self, rows, cols):
@@ -208,12 +213,14 @@ class PlanBuilder:
                 else:
                     self._free[i][0] = s + nbytes
                 self._live[s] = nbytes
-                return View(s, cols, 0, cols)
+                self._next_aid += 1
+                return View(s, cols, 0, cols, self._next_aid)
         s = self._top
         self._top += nbytes
         self.peak = max(self.peak, self._top)
         self._live[s] = nbytes
-        return View(s, cols, 0, cols)
+        self._next_aid += 1
+        return View(s, cols, 0, cols, self._next_aid)
 
     def free(self, view):
         s = view.off
@@ -248,7 +255,7 @@ class PlanBuilder:
         o.src, o.in_ld, o.in_coff, o.Cin = v.off, v.ld, v.coff, cols
         o.dst, o.out_ld, o.out_coff, o.Cout = dst.off, dst.ld, dst.coff, cp
         o.Tin, o.Fin = rows_per_utt, 1
-        self.ops.append(o)
+        self._emit(o, dst=dst, src=v)
         return dst
 
     def output_view(self, cols, rows):
@@ -314,7 +321,7 @@ class PlanBuilder:
             assert sum_into.C == dst.C and not c1
             o.sum, o.sum_ld, o.sum_coff = sum_into.off, sum_into.ld, sum_into.coff
         self._check_conv(o)
-        self.ops.append(o)
+        self._emit(o, dst=dst, src=src, src2=src2, summed=sum_into)
         return o
 
     @staticmethod
@@ -341,7 +348,7 @@ class PlanBuilder:
         o.eps = eps
         if seg_len is not None:
             o.seg_len, o.n_seg = seg_len, n_seg
-        self.ops.append(o)
+        self._emit(o, dst=dst, untracked=True)
         return o
 
     def asp_pool(self, x, logits, dst, T, eps=1e-12, mean_only=False):
@@ -352,7 +359,7 @@ class PlanBuilder:
         o.dst, o.out_ld, o.out_coff = dst.off, dst.ld, dst.coff
         o.Tin = T
         o.eps = eps
-        self.ops.append(o)
+        self._emit(o, dst=dst, untracked=True)
         return o
 
     def pool2d(self, src, dst, mode, Tin, Fin, Tout, Fout, k=3, stride=1, pad=1):
@@ -364,7 +371,7 @@ class PlanBuilder:
         o.KT = o.KF = k
         o.sT = o.sF = stride
         o.padT = o.padF = pad
-        self.ops.append(o)
+        self._emit(o, dst=dst, src=src)
         return o
 
     def ew(self, mode, x, dst, rows_per_utt, gate=None, res=None, y=None, att=None, act2=L.ACT_NONE):
@@ -382,8 +389,45 @@ class PlanBuilder:
             o.src2, o.src2_ld, o.src2_coff = y.off, y.ld, y.coff
         if att is not None:
             o.res, o.res_ld, o.res_coff = att.off, att.ld, att.coff
-        self.ops.append(o)
+        self._emit(o, dst=dst, src=x)
         return o
+
+    # ---- amax slots of the fp16 split (include/vpb200.h: vp_op.amax_out / amax_in) ----
+    def _emit(self, o, dst=None, src=None, src2=None, summed=None, untracked=False):
+        aid = lambda v: getattr(v, 'aid', None) if v is not None else None
+        self._meta.append(dict(dst=aid(dst), src=aid(src), src2=aid(src2), summed=aid(summed), untracked=untracked))
+        self.ops.append(o)
+        self._finalized = False
+
+    def finalize(self):
+        """Assign amax slots: one slot per workspace allocation that a CONV with an fp16 weight image reads as its
+        (whole) source; every op writing into that allocation maxes |y| into the slot, the CONV scales by it.  An
+        allocation written by an op that does not track amax (pooling kernels, accumulate-into views) gets no slot, so
+        its consumers stay on split TF32.  Idempotent."""
+        if self._finalized:
+            return self
+        for o in self.ops:
+            o.amax_out = o.amax_in = 0
+        bad = set()
+        for o, m in zip(self.ops, self._meta):
+            if m['untracked'] and m['dst'] is not None:
+                bad.add(m['dst'])
+            if m['summed'] is not None:
+                bad.add(m['summed'])
+        slots = {}
+        for o, m in zip(self.ops, self._meta):
+            if o.kind != L.OP_CONV or o.w_tc16_q <= 0 or m['src'] is None or m['src'] in bad:
+                continue
+            if o.pre_s >= 0 or o.src2_mode == L.SRC2_ADD:
+                continue                                    # source modes the fp16 kernel does not implement
+            if o.src2_mode == L.SRC2_CONCAT and m['src2'] != m['src']:
+                continue                                    # two tensors, one scale: only when they share an allocation
+            o.amax_in = slots.setdefault(m['src'], len(slots)) + 1
+        for o, m in zip(self.ops, self._meta):
+            if m['dst'] in slots:
+                o.amax_out = slots[m['dst']] + 1
+        self._finalized = True
+        return self
 
 
 class Program:
@@ -395,6 +439,7 @@ class Program:
         self.ws_bytes = max(pb.peak, ALIGN)
         self.in_floats, self.out_floats = pb.in_floats, pb.out_floats
         self.taps = pb.taps
+        pb.finalize()
         arr = (L.Op * self.n_ops)(*pb.ops)
         self._p = C.c_void_p()
         _check(engine.handle, L.lib().vp_program_create(engine.handle, arr, self.n_ops, self.ws_bytes,
