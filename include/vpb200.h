@@ -213,6 +213,16 @@ int vp_program_op_info(const vp_program* p, int32_t i, int32_t* kind, int64_t* M
  * staging matrix dst[n, lmax] with n_threads worker threads -- the pad-to-longest loop of predict.py:248-254. */
 int vp_host_gather_pad(const float* const* srcs, const int32_t* lens, int32_t n, int32_t lmax, float* dst,
                        int32_t n_threads);
+/* cudaMemsetAsync(device_ptr, 0, nbytes) on `stream`: zero padding of feature batches by hosts that must not bring
+ * their own kernels (collate_fn.py:12-19 pads FEATURES, not waveforms). */
+int vp_device_zero(void* device_ptr, size_t nbytes, void* stream);
+
+/* Cosine score matrix scores[i, j] = <a_i, b_j> / (|a_i| |b_j|), a [n, D], b [m, D], scores [n, m] (device, row-major):
+ * the scoring step of the callers around the embedding path -- retrieval against the enrolled speaker means
+ * (predict.py:169-183), evaluate's trial-vs-enrol scores (trainer.py:454-461) and the diarization similarity matrix
+ * (infer_utils/speaker_diarization.py:254-257). */
+int vp_cosine_scores(vp_handle* h, const float* a, int32_t n, const float* b, int32_t m, int32_t D, float* scores, void* stream);
+
 /* Staging half of predict_batch (predict.py:244-255) as ONE native call: worker threads gather slices of slice_rows
  * utterances into the zero-padded PINNED matrix staging[n, lmax]; the calling thread issues
  * cudaMemcpyAsync(staging slice -> device_dst slice) on copy_stream as soon as a slice is complete, so the H2D transfer

@@ -89,8 +89,8 @@ def kaldi_mel_banks(num_bins, padded_size, sample_freq, low_freq, high_freq):
     return torch.max(torch.zeros(1), torch.min(up, down))
 
 
-def kaldi_fbank(waveform, **kwargs):
-    """One utterance: waveform [L] (or [1, L]) float32 -> [m, num_mel_bins] (kaldi.py:514-645).
+def _kaldi_fbank_fp32(waveform, **kwargs):
+    """One utterance: waveform [L] (or [1, L]) float32 -> [m, num_mel_bins] (kaldi.py:514-645), fp32 like the reference.
 
     Supported subset: dither == 0, vtln_warp == 1, snip_edges True, use_energy False, subtract_mean False
     (everything the shipped configs use; other values raise NotImplementedError)."""
@@ -127,9 +127,44 @@ def kaldi_fbank(waveform, **kwargs):
     return mel
 
 
-def kaldi_fbank_batch(waveforms, **kwargs):
+def kaldi_fbank(waveform, exact_spectrum=False, **kwargs):
+    """One utterance: waveform [L] (or [1, L]) float32 -> [m, num_mel_bins] (kaldi.py:514-645).
+
+    ``exact_spectrum=True`` evaluates the SAME formula on the SAME fp32 windowed frames, but the rFFT, the power spectrum
+    and the mel projection in float64 (rounded to fp32 once, before the log): the exact value of what the reference's
+    fp32 pipeline approximates.  Tests use it to measure the reference's own rounding error -- the floor below which no
+    implementation can agree with the reference (tools/fbank_precision_study.py)."""
+    if not exact_spectrum:
+        return _kaldi_fbank_fp32(waveform, **kwargs)
+    a = fbank_args(**kwargs)
+    w = torch.as_tensor(waveform, dtype=torch.float32)
+    if w.dim() == 2:
+        w = w[max(a['channel'], 0)]
+    shift, size, padded = frame_geometry(a['sample_frequency'], a['frame_shift'], a['frame_length'], a['round_to_power_of_two'])
+    m = num_frames(w.numel(), size, shift)
+    frames = w.as_strided((m, size), (shift, 1))
+    if a['remove_dc_offset']:
+        frames = frames - frames.mean(dim=1, keepdim=True)
+    c = a['preemphasis_coefficient']
+    if c != 0.0:
+        frames = frames - c * torch.cat([frames[:, :1], frames[:, :-1]], dim=1)
+    frames = frames * feature_window(a['window_type'], size, a['blackman_coeff']).unsqueeze(0)
+    if padded != size:
+        frames = torch.nn.functional.pad(frames, (0, padded - size))
+    spec = torch.fft.rfft(frames.double()).abs()
+    if a['use_power']:
+        spec = spec.pow(2.0)
+    banks = kaldi_mel_banks(a['num_mel_bins'], padded, a['sample_frequency'], a['low_freq'], a['high_freq'])
+    banks = torch.nn.functional.pad(banks.to(torch.float32), (0, 1)).double()
+    mel = torch.mm(spec, banks.T).float()
+    if a['use_log_fbank']:
+        mel = torch.max(mel, torch.tensor(F32_EPS)).log()
+    return mel
+
+
+def kaldi_fbank_batch(waveforms, exact_spectrum=False, **kwargs):
     """mvector KaldiFbank.forward (featurizer.py:119-132): per-utterance loop -> [B, F, T]."""
-    outs = [kaldi_fbank(w, **kwargs).transpose(0, 1) for w in waveforms]
+    outs = [kaldi_fbank(w, exact_spectrum=exact_spectrum, **kwargs).transpose(0, 1) for w in waveforms]
     return torch.stack(outs)
 
 
@@ -267,15 +302,15 @@ def mfcc(waveforms, **kwargs):
 # ---------------------------------------------------------------------------------------------
 # AudioFeaturizer.forward
 # ---------------------------------------------------------------------------------------------
-def featurize(waveforms, input_lens_ratio=None, feature_method='Fbank', method_args=None):
+def featurize(waveforms, input_lens_ratio=None, feature_method='Fbank', method_args=None, exact_spectrum=False):
     """featurizer.py:53-91: feat [B,F,T] -> transpose -> subtract time-mean over ALL T frames -> zero
-    frames t >= round(ratio*T).  Returns [B, T, F] float32."""
+    frames t >= round(ratio*T).  Returns [B, T, F] float32.  ``exact_spectrum`` (Fbank only): see kaldi_fbank."""
     method_args = dict(method_args or {})
     w = torch.as_tensor(waveforms, dtype=torch.float32)
     if w.dim() == 1:
         w = w.unsqueeze(0)
     if feature_method == 'Fbank':
-        feat = kaldi_fbank_batch(w, **method_args)
+        feat = kaldi_fbank_batch(w, exact_spectrum=exact_spectrum, **method_args)
     elif feature_method == 'MelSpectrogram':
         feat = mel_spectrogram(w, **method_args)
     elif feature_method == 'Spectrogram':

@@ -14,7 +14,27 @@ from conftest import load_golden, rel_l2
 pytestmark = pytest.mark.gpu
 
 EMB_TOL = 1e-4          # north_star: "within 1e-4 relative fp32"
-FBANK_ABS_TOL = 5e-4    # on log-mel values spanning about [-16, +6]; SURVEY.md 8d asks <= ~1e-4 typical
+# Log-mel parity (values span about [-16, +6]).  The reference's own fp32 FFT is up to ~6e-4 away from the exact value of
+# its formula on white-noise input (pre-emphasis leaves the low bins 30 dB below the frame energy and the log turns their
+# relative error into an absolute one; tools/fbank_precision_study.py), so |ours - reference| cannot be bounded below
+# that by ANY implementation.  The front-end kernel therefore computes the spectrum in fp64 and the tests check
+#   (1) |ours - exact| <= FBANK_EXACT_TOL   (exact = oracle with exact_spectrum=True: same fp32 frames, fp64 spectrum)
+#   (2) |ours - reference| <= |reference - exact| + FBANK_EXACT_TOL   (never farther than the reference's own rounding)
+FBANK_EXACT_TOL = 3e-5
+FBANK_ABS_TOL = 2e-3    # hard cap on |ours - reference| whatever the input
+
+
+def _fbank_three_way(got, waves, ratio, args):
+    """-> (|ours - exact|, |ours - ref|, |ref - exact|) max-abs on CMN'd log-mel features."""
+    from oracle import frontend as ofe
+    ref = ofe.featurize(waves, ratio, 'Fbank', args)
+    exact = ofe.featurize(waves, ratio, 'Fbank', args, exact_spectrum=True)
+    assert got.shape == ref.shape
+    e_got, e_ref, d = (got - exact).abs().max().item(), (ref - exact).abs().max().item(), (got - ref).abs().max().item()
+    print(f'fbank: |ours-exact| {e_got:.2e}  |ours-ref| {d:.2e}  |ref-exact| {e_ref:.2e}')
+    assert e_got <= FBANK_EXACT_TOL, (e_got, e_ref)
+    assert d <= e_ref + FBANK_EXACT_TOL and d < FBANK_ABS_TOL, (d, e_ref)
+    return e_got, d, e_ref
 
 
 def _model(name, fdim, margs, sd, engine_pref=None):
@@ -41,9 +61,8 @@ def test_fbank_single_lengths(n):
     w = torch.randn(2, n, generator=g) * 0.1
     fz = _featurizer(dict(feature_method='Fbank', method_args=args))
     got = fz(w).cpu()
-    ref = ofe.featurize(w, None, 'Fbank', args)
-    assert got.shape == ref.shape == (2, 1 + (n - 400) // 160, 80)
-    assert (got - ref).abs().max().item() < FBANK_ABS_TOL
+    assert got.shape == (2, 1 + (n - 400) // 160, 80)
+    _fbank_three_way(got, w, None, args)
 
 
 def test_fbank_ragged_batch_semantics():
@@ -56,8 +75,7 @@ def test_fbank_ragged_batch_semantics():
     ref = ofe.featurize(x, ratio, 'Fbank', args)
     fz = _featurizer(dict(feature_method='Fbank', method_args=args))
     got = fz(torch.from_numpy(x), torch.from_numpy(ratio)).cpu()
-    assert got.shape == ref.shape
-    assert (got - ref).abs().max().item() < FBANK_ABS_TOL
+    _fbank_three_way(got, x, ratio, args)
     keep = torch.round(torch.from_numpy(ratio) * ref.shape[1]).long()
     for i, k in enumerate(keep.tolist()):
         assert torch.all(got[i, k:] == 0)          # masked frames are exactly zero
@@ -654,3 +672,20 @@ def test_c_host_example_matches_python_host(tmp_path):
     got = np.fromfile(str(tmp_path / 'emb.f32'), dtype=np.float32).reshape(B, 192)
     ref = model(feats.cuda()).cpu().numpy()
     assert np.array_equal(got, ref)                  # same kernels, same program -> bit identical
+
+
+@pytest.mark.parametrize('n,m,D', [(1, 1, 192), (7, 33, 192), (100, 257, 512), (3, 5, 36)])
+def test_cosine_scores_on_device(n, m, D):
+    """vp_cosine_scores (retrieval predict.py:169-183, evaluate trainer.py:454-461, diarization affinity
+    speaker_diarization.py:254-257) against sklearn-style normalise-then-matmul in float64."""
+    from mvector.engine import Engine
+    rng = np.random.default_rng(n * 1000 + m)
+    a = rng.standard_normal((n, D)).astype(np.float32) * 3
+    b = rng.standard_normal((m, D)).astype(np.float32) * 0.01
+    eng = Engine()
+    got = eng.cosine_scores(a, b).cpu().numpy()
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    ref = (a64 / np.linalg.norm(a64, axis=1, keepdims=True)) @ (b64 / np.linalg.norm(b64, axis=1, keepdims=True)).T
+    assert got.shape == (n, m) and np.abs(got - ref).max() < 2e-6
+    assert torch.equal(eng.cosine_scores(a, b), eng.cosine_scores(a, b))          # deterministic
+    eng.close()

@@ -283,6 +283,21 @@ def test_evaluate_host_logic_with_oracle_backend(tmp_path, manifest):
                                                   'trials_list': lists['trials']}})
     tr.use_gpu, tr.stop_eval, tr._device = False, False, torch.device('cpu')
     tr.audio_featurizer, tr.model = Fz(), Net()
+
+    # the two device steps of the glue (memset + D2D padding, vp_cosine_scores) get numpy stand-ins here; the real ones are
+    # covered on hardware by tests/test_gpu_parity.py::test_evaluate_matches_reference_golden
+    def pad(items):
+        x = torch.zeros(len(items), max(f.shape[0] for f in items), items[0].shape[1])
+        for i, f in enumerate(items):
+            x[i, :f.shape[0]] = f
+        return x
+
+    def score(t, e):
+        tn = t / np.linalg.norm(t, axis=1, keepdims=True)
+        en = e / np.linalg.norm(e, axis=1, keepdims=True)
+        return (tn @ en.T).astype(np.float32)
+
+    tr._zero_pad_features, tr._cosine_scores = pad, score
     captured = {}
     real = mt.compute_fnr_fpr
 

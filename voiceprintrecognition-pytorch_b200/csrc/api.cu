@@ -27,7 +27,7 @@ struct vp_handle {
   bool fe_set = false;
   vp_frontend_desc fe{};
   float* d_window = nullptr;
-  float2* d_twiddle = nullptr;
+  double2* d_twiddle = nullptr;
   int* d_mel_start = nullptr;
   int* d_mel_count = nullptr;
   int* d_mel_off = nullptr;
@@ -146,20 +146,20 @@ int vp_frontend_set(vp_handle* h, const vp_frontend_desc* d, const float* window
   }
   CUDA_TRY(h, cudaSetDevice(h->device));
   free_frontend(h);
-  std::vector<float2> tw(N);
+  std::vector<double2> tw(N);
   for (int k = 0; k < N; ++k) {
     double a = -2.0 * M_PI * (double)k / (double)N;
-    tw[k] = make_float2((float)cos(a), (float)sin(a));
+    tw[k] = make_double2(cos(a), sin(a));
   }
   const int F = d->n_mels;
   CUDA_TRY(h, cudaMalloc(&h->d_window, sizeof(float) * d->win_length));
-  CUDA_TRY(h, cudaMalloc(&h->d_twiddle, sizeof(float2) * N));
+  CUDA_TRY(h, cudaMalloc(&h->d_twiddle, sizeof(double2) * N));
   CUDA_TRY(h, cudaMalloc(&h->d_mel_start, sizeof(int) * F));
   CUDA_TRY(h, cudaMalloc(&h->d_mel_count, sizeof(int) * F));
   CUDA_TRY(h, cudaMalloc(&h->d_mel_off, sizeof(int) * F));
   CUDA_TRY(h, cudaMalloc(&h->d_mel_w, sizeof(float) * (n_w > 0 ? n_w : 1)));
   CUDA_TRY(h, cudaMemcpy(h->d_window, window, sizeof(float) * d->win_length, cudaMemcpyHostToDevice));
-  CUDA_TRY(h, cudaMemcpy(h->d_twiddle, tw.data(), sizeof(float2) * N, cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->d_twiddle, tw.data(), sizeof(double2) * N, cudaMemcpyHostToDevice));
   CUDA_TRY(h, cudaMemcpy(h->d_mel_start, mel_start, sizeof(int) * F, cudaMemcpyHostToDevice));
   CUDA_TRY(h, cudaMemcpy(h->d_mel_count, mel_count, sizeof(int) * F, cudaMemcpyHostToDevice));
   CUDA_TRY(h, cudaMemcpy(h->d_mel_off, mel_off, sizeof(int) * F, cudaMemcpyHostToDevice));
@@ -219,6 +219,7 @@ static int run_frontend(vp_handle* h, int want_kind, int want_post, const float*
   p.F = h->fe.n_mels; p.remove_dc = h->fe.remove_dc; p.power = h->fe.power; p.use_log = h->fe.use_log;
   p.fpb = FPB; p.nblk = (T + FPB - 1) / FPB;
   p.preemph = h->fe.preemph; p.log_floor = h->fe.log_floor; p.db_mult = h->fe.db_mult; p.cta_max = nullptr;
+  frontend_plan(p);
   if (h->fe.post == 1) {
     MfccParams m;
     float* cta_max = scratch + round4((size_t)B * p.nblk * h->fe.n_out);
@@ -687,6 +688,19 @@ int vp_embed_wave(vp_program* p, const float* wave, int32_t B, int32_t Lpad, con
   int r = run_frontend(p->h, -1, -1, wave, B, Lpad, keep, feats_scratch, fe_scratch, (cudaStream_t)stream);
   if (r != VP_OK) return r;
   return vp_embed(p, feats_scratch, emb, stream);
+}
+
+int vp_device_zero(void* device_ptr, size_t nbytes, void* stream) {
+  if (!device_ptr) return VP_ERR_INVALID;
+  return cudaMemsetAsync(device_ptr, 0, nbytes, (cudaStream_t)stream) == cudaSuccess ? VP_OK : VP_ERR_CUDA;
+}
+
+int vp_cosine_scores(vp_handle* h, const float* a, int32_t n, const float* b, int32_t m, int32_t D, float* scores, void* stream) {
+  if (!h) return VP_ERR_INVALID;
+  if (!a || !b || !scores || n < 1 || m < 1 || D < 1) return fail(h, VP_ERR_INVALID, "null/empty argument");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, launch_cosine_scores(a, b, scores, n, m, D, (cudaStream_t)stream));
+  return VP_OK;
 }
 
 int vp_program_peek(vp_program* p, int64_t off, size_t nbytes, void* dst, void* stream) {

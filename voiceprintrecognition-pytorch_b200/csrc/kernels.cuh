@@ -6,12 +6,14 @@ namespace vpb {
 
 struct FrontendParams {
   const float* wave; float* feats; float* partial;
-  const float* window; const float2* twiddle;
+  const float* window; const double2* twiddle;   // twiddle[k] = exp(-2 pi i k / N) in fp64
   const int* mel_start; const int* mel_count; const int* mel_off; const float* mel_w;
   int B, L, T, kind, N, WL, hop, F, remove_dc, power, use_log, fpb, nblk;
   float preemph, log_floor, db_mult;
   float* cta_max;      // non-null: MFCC mel stage (per-CTA maxima instead of CMN partial sums)
+  int n_pass, radix[12], G;   // FFT pass plan + threads per FFT group (frontend_plan)
 };
+void frontend_plan(FrontendParams& p);
 
 // MFCC tail: mel [B,T,M] dB values -> clamp(max - top_db) -> DCT [M,K] -> feats [B,T,K] + CMN partial sums.
 struct MfccParams {
@@ -47,6 +49,7 @@ struct PoolParams {
   unsigned* amax_out;
 };
 cudaError_t launch_pool2d(const PoolParams& p, cudaStream_t stream);
+cudaError_t launch_cosine_scores(const float* a, const float* b, float* out, int n, int m, int D, cudaStream_t stream);
 
 cudaError_t launch_frontend(const FrontendParams& p, const int* keep, cudaStream_t stream);
 cudaError_t launch_frontend_mfcc(const FrontendParams& p, const MfccParams& m, const int* keep, cudaStream_t stream);

@@ -47,6 +47,20 @@ class Engine:
         blob = np.ascontiguousarray(blob, dtype=np.float32)
         _check(self._h, L.lib().vp_weights_load(self._h, blob.ctypes.data_as(C.c_void_p), blob.nbytes))
 
+    def cosine_scores(self, a, b):
+        """[n, D] x [m, D] -> device tensor [n, m] of cosine similarities (vp_cosine_scores); inputs: numpy / torch."""
+        ta = torch.as_tensor(a, dtype=torch.float32).to(self.device).contiguous()
+        tb = torch.as_tensor(b, dtype=torch.float32).to(self.device).contiguous()
+        if ta.dim() == 1:
+            ta = ta.unsqueeze(0)
+        if tb.dim() == 1:
+            tb = tb.unsqueeze(0)
+        assert ta.shape[1] == tb.shape[1]
+        out = torch.empty(ta.shape[0], tb.shape[0], dtype=torch.float32, device=self.device)
+        _check(self._h, L.lib().vp_cosine_scores(self._h, C.c_void_p(ta.data_ptr()), ta.shape[0], C.c_void_p(tb.data_ptr()),
+                                                 tb.shape[0], ta.shape[1], C.c_void_p(out.data_ptr()), self.stream_ptr()))
+        return out
+
     def close(self):
         if self._h:
             for p in self._programs:

@@ -25,8 +25,11 @@ class SpectralCluster:
         self.max_num_spks = max_num_spks
         self.pval = pval
 
+    sim_fn = None          # optional device scorer X -> [n, n] cosine matrix (MVectorPredictor installs vp_cosine_scores)
+
     def __call__(self, X, oracle_num=None):
-        affinity = self.p_pruning(self.get_sim_mat(X))
+        sim = self.get_sim_mat(X) if self.sim_fn is None else np.array(self.sim_fn(np.asarray(X, dtype=np.float32)), dtype=np.float32)
+        affinity = self.p_pruning(sim)
         affinity = 0.5 * (affinity + affinity.T)
         emb, k = self.get_spec_embs(self.get_laplacian(affinity), oracle_num)
         return self.cluster_embs(emb, k)
@@ -79,6 +82,10 @@ class SpeakerDiarization(object):
         self.sample_rate = sample_rate
         self.merge_threshold = merge_threshold
         self.spectral_cluster = SpectralCluster()
+
+    def set_similarity(self, sim_fn):
+        """Install a device scorer for the clustering's cosine affinity matrix (None: numpy on the host)."""
+        self.spectral_cluster.sim_fn = sim_fn
 
     # ------------------------------------------------------------------ segmentation
     def segments_audio(self, audio_segment):

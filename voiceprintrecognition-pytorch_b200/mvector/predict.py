@@ -63,6 +63,8 @@ class MVectorPredictor:
         self._ws_per_utt = {}
 
         self.speaker_diarize = SpeakerDiarization()
+        # similarity matrix of the spectral clustering (speaker_diarization.py:254-257) on the device
+        self.speaker_diarize.set_similarity(lambda X: self._engine.cosine_scores(X, X).cpu().numpy())
 
         self.audio_feature = None
         self.audio_feature_mean = None
@@ -144,10 +146,9 @@ class MVectorPredictor:
     def __retrieval(self, np_feature):
         if isinstance(np_feature, list):
             np_feature = np.array(np_feature)
-        q = self.normalize_features(np_feature.astype(np.float32))
-        db = self.audio_feature_mean / np.linalg.norm(self.audio_feature_mean, axis=1, keepdims=True)
+        sims = self._engine.cosine_scores(np_feature.astype(np.float32), self.audio_feature_mean).cpu().numpy()
         labels = []
-        for sim in q @ db.T:                                   # cosine similarity (predict.py:169-183)
+        for sim in sims:                                       # cosine similarity on the device (predict.py:169-183)
             idx = int(np.argmax(sim))
             s = sim[idx]
             labels.append([self.users_name_mean[idx], round(float(s), 5)] if s >= self.threshold else [None, None])

@@ -110,58 +110,71 @@ class MVectorTrainer(object):
         self.model = build_model(input_size=self.audio_featurizer.feature_dim, configs=self.configs)
         self.model.engine = self._engine
 
-    def _eval_items(self, data_list):
-        """Features of one list in the reference's eval order: [(feature [T, F] on the device, label)]."""
+    def _eval_order(self, data_list):
+        """Reference eval order (sort_list, reader.py:127-144): entries sorted by duration (frames for .npy features).  Only
+        (path, label, length) is kept -- audio is decoded again, one batch at a time, when it is embedded."""
+        with open(data_list, 'r', encoding='utf-8') as f:
+            lines = f.readlines()
+        entries, lengths = [], []
+        for line in lines:
+            path, label = line.replace('\n', '').split('\t')
+            if path.endswith('.npy'):
+                lengths.append(np.load(path, mmap_mode='r').shape[0])
+            else:
+                lengths.append(AudioSegment.from_file(path).duration)
+            entries.append((path, int(label)))
+        return [entries[i] for i in np.argsort(lengths)]
+
+    def _eval_feature(self, path):
+        """One item's feature [T, F] on the device (reader.py:76-100, eval mode)."""
         ds = self.configs.dataset_conf.get('dataset', {})
         sample_rate = ds.get('sample_rate', 16000)
         use_db, target_db = ds.get('use_dB_normalization', True), ds.get('target_dB', -20)
         max_duration = self.configs.dataset_conf.eval_conf.max_duration          # trainer.py:126
-        # get_crop_feature_len (reader.py:119-124): frames of a max_duration-long waveform
-        max_feature_len = self.audio_featurizer.num_frames(int(max_duration * sample_rate))
-        with open(data_list, 'r', encoding='utf-8') as f:
-            lines = f.readlines()
-        loaded, lengths = [], []
-        for line in lines:                                                       # sort_list, reader.py:127-144
-            path, label = line.replace('\n', '').split('\t')
-            if path.endswith('.npy'):
-                obj = np.load(path)
-                lengths.append(obj.shape[0])
-            else:
-                obj = AudioSegment.from_file(path)
-                lengths.append(obj.duration)
-            loaded.append((path, int(label), obj))
-        items = []
-        for i in np.argsort(lengths):
-            path, label, obj = loaded[i]
-            if path.endswith('.npy'):                                            # reader.py:76-81
-                feature = torch.from_numpy(np.asarray(obj[:max_feature_len], dtype=np.float32)).to(self._device)
-            else:
-                seg = obj
-                if seg.sample_rate != sample_rate:
-                    seg.resample(sample_rate)
-                if use_db:
-                    seg.normalize(target_db=target_db)
-                if seg.duration > max_duration:                                  # crop(mode='eval'): from the start
-                    seg.samples = seg.samples[:int(max_duration * seg.sample_rate)]
-                feature = self.audio_featurizer(torch.from_numpy(seg.samples)).squeeze(0)
-            items.append((feature, label))
-        return items
+        if path.endswith('.npy'):                                                # reader.py:76-81
+            # get_crop_feature_len (reader.py:119-124): frames of a max_duration-long waveform
+            max_feature_len = self.audio_featurizer.num_frames(int(max_duration * sample_rate))
+            return torch.from_numpy(np.asarray(np.load(path)[:max_feature_len], dtype=np.float32)).to(self._device)
+        seg = AudioSegment.from_file(path)
+        if seg.sample_rate != sample_rate:
+            seg.resample(sample_rate)
+        if use_db:
+            seg.normalize(target_db=target_db)
+        if seg.duration > max_duration:                                          # crop(mode='eval'): from the start
+            seg.samples = seg.samples[:int(max_duration * seg.sample_rate)]
+        return self.audio_featurizer(torch.from_numpy(seg.samples)).squeeze(0)
 
     def _embed_list(self, data_list):
-        items = self._eval_items(data_list)
+        """Embeddings of one list in eval order, one eval_conf.batch_size batch at a time: decode -> featurize singly ->
+        zero-pad the FEATURES to the batch's longest item (collate_fn.py:12-19) -> backbone.  Host and device memory stay
+        O(batch); the padding is a memset + device-to-device copies (no library kernel on the path)."""
+        entries = self._eval_order(data_list)
         bs = self.configs.dataset_conf.eval_conf.batch_size
         feats, labels = [], []
-        for s in range(0, len(items), bs):
+        for s in range(0, len(entries), bs):
             if self.stop_eval:
                 break
-            chunk = items[s:s + bs]
-            tmax = max(f.shape[0] for f, _ in chunk)
-            x = torch.zeros((len(chunk), tmax, chunk[0][0].shape[1]), dtype=torch.float32, device=self._device)
-            for i, (f, _) in enumerate(chunk):                                   # collate_fn.py:12-19
-                x[i, :f.shape[0]] = f
-            feats.append(self.model(x).cpu().numpy())
+            chunk = [(self._eval_feature(path), label) for path, label in entries[s:s + bs]]
+            feats.append(self.model(self._zero_pad_features([f for f, _ in chunk])).cpu().numpy())
             labels.extend(lb for _, lb in chunk)
         return np.concatenate(feats), np.asarray(labels, dtype=np.int32)
+
+    def _zero_pad_features(self, items):
+        """collate_fn.py:12-19 on the device: [T_i, F] features -> zero-padded [B, Tmax, F] (memset + D2D row copies)."""
+        import ctypes as C
+        from . import _lib as L
+        tmax = max(f.shape[0] for f in items)
+        x = torch.empty((len(items), tmax, items[0].shape[1]), dtype=torch.float32, device=self._device)
+        rc = L.lib().vp_device_zero(C.c_void_p(x.data_ptr()), x.numel() * 4, self._engine.stream_ptr())
+        if rc != L.VP_OK:
+            raise L.VpError(rc, 'vp_device_zero failed')
+        for i, f in enumerate(items):
+            x[i, :f.shape[0]].copy_(f)                                           # contiguous rows: a D2D memcpy
+        return x
+
+    def _cosine_scores(self, trials, enroll):
+        """trainer.py:454-461 (sklearn cosine_similarity of every trial against every enrolment) on the device."""
+        return self._engine.cosine_scores(trials, enroll).cpu().numpy()
 
     def evaluate(self, resume_model=None, save_image_path=None):
         """评估模型 (trainer.py:403-485) -> (eer, min_dcf, threshold)"""
@@ -179,10 +192,8 @@ class MVectorTrainer(object):
         if self.stop_eval:
             return -1, -1, -1
         logger.info('开始对比音频特征...')
-        # cosine_similarity of every trial against every enrolment (trainer.py:454-461), trial-major order
-        en = enroll_features / np.linalg.norm(enroll_features, axis=1, keepdims=True)
-        tn = trials_features / np.linalg.norm(trials_features, axis=1, keepdims=True)
-        all_score = (tn @ en.T).astype(np.float32).reshape(-1)
+        # cosine_similarity of every trial against every enrolment (trainer.py:454-461), trial-major order, on the device
+        all_score = self._cosine_scores(trials_features, enroll_features).reshape(-1)
         all_labels = (trials_labels[:, None] == enroll_labels[None, :]).astype(np.int32).reshape(-1)
         fnr, fpr, thresholds = compute_fnr_fpr(all_score, all_labels)
         eer, threshold = compute_eer(fnr, fpr, all_score)
