@@ -23,6 +23,7 @@ struct vp_handle {
   // sized to the largest live program, so serving ragged lengths costs max(ws), not sum(ws), of device memory
   char* d_arena = nullptr;
   size_t arena_bytes = 0;
+  cudaStream_t cap_stream = nullptr;   // private stream CUDA graphs are captured on (the caller's may be the legacy default)
   // front-end
   bool fe_set = false;
   vp_frontend_desc fe{};
@@ -42,6 +43,13 @@ struct vp_program {
   size_t ws_bytes = 0, in_floats = 0, out_floats = 0;
   int launches = 0;
   int B = 0;                  // utterances (every op of a program agrees on it)
+  // CUDA graph of one vp_embed (all ops + the slot memset), keyed on the pointers baked into its nodes
+  cudaGraphExec_t gexec = nullptr;
+  const float* g_feats = nullptr;
+  float* g_emb = nullptr;
+  char* g_arena = nullptr;
+  int runs = 0, g_miss = 0;
+  bool g_off = false;
   int n_slots = 0;            // amax slots (uint32 each) behind the workspace, zeroed at the start of every run
   size_t arena_need() const { return ws_bytes + (((size_t)n_slots * 4 + 255) & ~(size_t)255); }
   unsigned* slot(int32_t q) const { return q > 0 ? reinterpret_cast<unsigned*>(h->d_arena + ws_bytes) + (q - 1) : nullptr; }
@@ -112,6 +120,7 @@ void vp_destroy(vp_handle* h) {
   free_frontend(h);
   cudaFree(h->d_weights);
   cudaFree(h->d_arena);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   delete h;
 }
 
@@ -521,6 +530,8 @@ int vp_program_create(vp_handle* h, const vp_op* ops, int32_t n_ops, size_t ws_b
 }
 
 void vp_program_destroy(vp_program* p) {
+  if (!p) return;
+  if (p->gexec) cudaGraphExecDestroy(p->gexec);
   delete p;                   // host state only: the workspace is the handle's shared arena
 }
 
@@ -561,8 +572,7 @@ static void fill_conv(const vp_program* p, const vp_op& o, const float* feats, f
 }
 
 static int run_ops(vp_program* p, const float* feats, float* emb, cudaStream_t st, cudaEvent_t* evs) {
-  vp_handle* h = p->h;
-  CUDA_TRY(h, cudaSetDevice(h->device));     // launch attributes / SM counts are looked up for the current device
+  vp_handle* h = p->h;                       // callers have made h->device current (launch attributes are per device)
   if (p->n_slots > 0) CUDA_TRY(h, cudaMemsetAsync(h->d_arena + p->ws_bytes, 0, (size_t)p->n_slots * 4, st));
   for (size_t i = 0; i < p->ops.size(); ++i) {
     const vp_op& o = p->ops[i];
@@ -635,9 +645,58 @@ static int run_ops(vp_program* p, const float* feats, float* emb, cudaStream_t s
   return VP_OK;
 }
 
+// VPB_GRAPH=0: always enqueue the ops one by one
+static bool graphs_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VPB_GRAPH"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
+
+// One vp_embed = one cudaGraphLaunch: the program's launches (tens for the TDNNs, hundreds for CAM++ / the 2-D nets) are
+// captured once per (feats, emb, arena) pointer triple on the handle's private stream -- the programmatic (PDL) edges
+// between the kernels are kept by the capture -- and replayed on the caller's stream.  The first run of a program is
+// always eager (it configures per-kernel attributes, which must not happen inside a capture).
+static int embed_graph(vp_program* p, const float* feats, float* emb, cudaStream_t st) {
+  vp_handle* h = p->h;
+  if (!p->gexec || p->g_feats != feats || p->g_emb != emb || p->g_arena != h->d_arena) {
+    if (p->gexec && ++p->g_miss > 16) {            // a caller that never reuses its buffers gains nothing from re-capturing
+      p->g_off = true;
+      return run_ops(p, feats, emb, st, nullptr);
+    }
+    if (!h->cap_stream && cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      p->g_off = true;
+      return run_ops(p, feats, emb, st, nullptr);
+    }
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      p->g_off = true;
+      return run_ops(p, feats, emb, st, nullptr);
+    }
+    const int r = run_ops(p, feats, emb, h->cap_stream, nullptr);
+    const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
+    cudaGraphExec_t ge = nullptr;
+    if (r != VP_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&ge, graph, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      p->g_off = true;                            // this program stays on plain stream launches
+      return run_ops(p, feats, emb, st, nullptr);
+    }
+    cudaGraphDestroy(graph);
+    if (p->gexec) cudaGraphExecDestroy(p->gexec);
+    p->gexec = ge;
+    p->g_feats = feats; p->g_emb = emb; p->g_arena = h->d_arena;
+  }
+  CUDA_TRY(h, cudaGraphLaunch(p->gexec, st));
+  return VP_OK;
+}
+
 int vp_embed(vp_program* p, const float* feats, float* emb, void* stream) {
   if (!p || !feats || !emb) return p ? fail(p->h, VP_ERR_INVALID, "null argument") : VP_ERR_INVALID;
-  return run_ops(p, feats, emb, (cudaStream_t)stream, nullptr);
+  CUDA_TRY(p->h, cudaSetDevice(p->h->device));
+  if (!graphs_enabled() || p->g_off || p->runs++ == 0) return run_ops(p, feats, emb, (cudaStream_t)stream, nullptr);
+  return embed_graph(p, feats, emb, (cudaStream_t)stream);
 }
 
 int vp_embed_profiled(vp_program* p, const float* feats, float* emb, void* stream, float* ms_per_op) {
@@ -645,6 +704,7 @@ int vp_embed_profiled(vp_program* p, const float* feats, float* emb, void* strea
   vp_handle* h = p->h;
   const size_t n = p->ops.size();
   std::vector<cudaEvent_t> evs(n + 1);
+  CUDA_TRY(h, cudaSetDevice(h->device));
   for (auto& e : evs) CUDA_TRY(h, cudaEventCreate(&e));
   int r = run_ops(p, feats, emb, (cudaStream_t)stream, evs.data());
   if (r == VP_OK) {

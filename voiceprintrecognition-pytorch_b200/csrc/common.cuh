@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "../../include/vpb200.h"
 
 namespace vpb {
@@ -24,6 +25,40 @@ struct PerDeviceSmem {
     if (d >= 0 && d < 64 && bytes > cfg[d]) cfg[d] = bytes;
   }
 };
+
+// ---- programmatic dependent launch (PDL) ----
+// Every kernel of the library starts with pdl_launch_dependents() -- the next kernel in the stream may be scheduled as
+// soon as all CTAs of this grid have started -- and calls pdl_wait() before its first access to mutable global memory
+// (activations, features, amax slots; weights / constant tables are immutable).  pdl_wait() returns when the
+// predecessor grid has COMPLETED and flushed, and the predecessor itself only completed after its own wait, so the
+// ordering of a stream of such kernels is transitive: all that overlaps is a kernel's prologue (block scheduling,
+// barrier / TMEM set-up, parameter loads) with the tail of the kernel before it.  Without the launch attribute both
+// instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// VPB_PDL=0 launches everything fully serialised (A/B runs)
+inline int pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VPB_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on;
+}
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-stream-serialisation attribute
+template <typename K, typename... A>
+inline void launch_pdl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, args...);      // errors are picked up by the caller's cudaGetLastError()
+}
 
 // Resolved (device-pointer) form of a vp_op, passed to kernels by value.
 struct ConvParams {

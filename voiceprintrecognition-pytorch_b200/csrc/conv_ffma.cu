@@ -18,6 +18,8 @@ constexpr int LDS_PAD = 4;
 
 template <int BN>
 __global__ void __launch_bounds__(256, 2) conv_ffma_kernel(const __grid_constant__ ConvParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                 // first access to mutable global memory comes after this
   constexpr int TN = BN / 16;           // columns per thread: 8, 4 or 2
   constexpr int LDA = BM + LDS_PAD;
   constexpr int LDB = BN + LDS_PAD;
@@ -161,6 +163,8 @@ __global__ void __launch_bounds__(256, 2) conv_ffma_kernel(const __grid_constant
 // each weight row, then a fixed-order butterfly reduction -> deterministic.  grid = (ceil(N/32), ceil(M/8)).
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) linear_small_m_kernel(const __grid_constant__ ConvParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                 // first access to mutable global memory comes after this
   // W tile [32 output columns][128 K] staged in shared memory once per CTA and K chunk, shared by the CTA's 8 rows
   __shared__ __align__(16) float ws[32][132];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -221,18 +225,18 @@ cudaError_t launch_conv_ffma(const ConvParams& p, cudaStream_t stream) {
   dim3 block(256);
   if (small_m_ok(p)) {
     dim3 grid((p.N + 31) / 32, (p.M + 7) / 8);
-    linear_small_m_kernel<<<grid, block, 0, stream>>>(p);
+    launch_pdl(linear_small_m_kernel, grid, block, 0, stream, p);
     return cudaGetLastError();
   }
   if (p.N > 64) {
     dim3 grid((p.M + BM - 1) / BM, (p.N + 127) / 128);
-    conv_ffma_kernel<128><<<grid, block, 0, stream>>>(p);
+    launch_pdl(conv_ffma_kernel<128>, grid, block, 0, stream, p);
   } else if (p.N > 32) {
     dim3 grid((p.M + BM - 1) / BM, 1);
-    conv_ffma_kernel<64><<<grid, block, 0, stream>>>(p);
+    launch_pdl(conv_ffma_kernel<64>, grid, block, 0, stream, p);
   } else {
     dim3 grid((p.M + BM - 1) / BM, 1);
-    conv_ffma_kernel<32><<<grid, block, 0, stream>>>(p);
+    launch_pdl(conv_ffma_kernel<32>, grid, block, 0, stream, p);
   }
   return cudaGetLastError();
 }
@@ -245,6 +249,8 @@ cudaError_t launch_conv_ffma(const ConvParams& p, cudaStream_t stream) {
 // One thread per output position x 4 output channels.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_c1_kernel(const __grid_constant__ ConvParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                 // first access to mutable global memory comes after this
   const int groups = p.N >> 2;
   const long long total = (long long)p.M * groups;
   const int taps = p.KT * p.KF;
@@ -285,7 +291,7 @@ cudaError_t launch_conv_c1(const ConvParams& p, cudaStream_t stream) {
   long long total = (long long)p.M * (p.N >> 2);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  conv_c1_kernel<<<blocks, 256, 0, stream>>>(p);
+  launch_pdl(conv_c1_kernel, blocks, 256, 0, stream, p);
   return cudaGetLastError();
 }
 

@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   constexpr int BKE = F16 ? 64 : BK;     // K elements per pipeline stage
   constexpr int KPT = F16 ? 8 : 4;       // K elements per producer thread and row
   using SlotT = typename std::conditional<F16, SlotH, Slot<MODE>>::type;
+  pdl_launch_dependents();                 // the next kernel's CTAs may be scheduled as SMs free up (see common.cuh)
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(8) uint64_t bars[2 * 8 + 4];     // full[S], empty[S], tmem_full[2], tmem_empty[2]
@@ -214,6 +215,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   if (C > 1) cluster_sync_all();           // peers' mbarriers are initialised before any remote arrive / multicast lands
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  // barrier init, TMEM allocation and the cluster handshake above overlap the tail of the previous kernel; everything
+  // below touches activations / amax slots / the output
+  pdl_wait();
 
   // work distribution: group g = (m_group, n_tile); CTA `crank` of the cluster takes M tile m_group*C + crank
   const int n_clusters = gridDim.x / C, cluster_id = blockIdx.x / C;
@@ -726,13 +730,15 @@ static cudaError_t launch_conv_tc_impl(const ConvParams& p, const float* w_img, 
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = C;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   if (f16) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, true>, p, a);
   else if (p.pre_s != nullptr) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, p, a);
   else if (p.src2_mode == VP_SRC2_ADD) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, p, a);

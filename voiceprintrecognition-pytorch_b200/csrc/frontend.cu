@@ -41,6 +41,8 @@ __device__ __forceinline__ void st2(double2* p, cd v) { *p = make_double2(v.x, v
 __device__ __forceinline__ void group_sync(int g, int G) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(G) : "memory"); }
 
 __global__ void __launch_bounds__(256) frontend_kernel(const __grid_constant__ FrontendParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                 // first access to mutable global memory comes after this
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = p.N, WL = p.WL, F = p.F;
   const int G = p.G;                                // threads per FFT (multiple of 32)
@@ -281,6 +283,8 @@ __global__ void __launch_bounds__(256) frontend_kernel(const __grid_constant__ F
 // mfcc[t, k] = sum_m mel_db[t, m] * dct[m, k] (create_dct, functional.py:640-667).  One CTA per (frame tile, utterance);
 // also emits the per-CTA column sums that cmn_mask_kernel turns into the CMN mean.
 __global__ void __launch_bounds__(256) mfcc_post_kernel(const __grid_constant__ MfccParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                 // first access to mutable global memory comes after this
   extern __shared__ __align__(16) float sm[];
   float* dct = sm;                              // [M][K]
   float* tile = dct + p.M * p.K;                // [fpb][M]
@@ -327,6 +331,8 @@ __global__ void __launch_bounds__(256) mfcc_post_kernel(const __grid_constant__ 
 // feats[b, t, :] -= mean_t(feats[b]) over ALL T frames, then frames t >= keep[b] are zeroed (featurizer.py:79-90).
 __global__ void __launch_bounds__(128) cmn_mask_kernel(float* feats, const float* partial, const int* keep, int T, int F,
                                                        int nblk, int rows_per_cta) {
+  pdl_launch_dependents();
+  pdl_wait();                 // first access to mutable global memory comes after this
   const int b = blockIdx.y;
   const int kp = keep ? keep[b] : T;
   const int t0 = blockIdx.x * rows_per_cta;
@@ -343,6 +349,8 @@ __global__ void __launch_bounds__(128) cmn_mask_kernel(float* feats, const float
 
 // out[0] = max(v[0..n)): the call-wide (or, sharded, the rank-wide) maximum of the per-CTA maxima of the MFCC mel stage
 __global__ void __launch_bounds__(256) max_reduce_kernel(const float* v, int n, float* out) {
+  pdl_launch_dependents();
+  pdl_wait();                 // first access to mutable global memory comes after this
   __shared__ float red[8];
   float m = -INFINITY;
   for (int i = threadIdx.x; i < n; i += 256) m = fmaxf(m, v[i]);
@@ -402,10 +410,10 @@ cudaError_t launch_frontend_mfcc_mel(const FrontendParams& p, float* max_out, cu
   cudaError_t e = ensure_frontend_smem(smem);
   if (e != cudaSuccess) return e;
   dim3 grid(p.nblk, p.B);
-  frontend_kernel<<<grid, 256, smem, stream>>>(p);
+  launch_pdl(frontend_kernel, grid, 256, smem, stream, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  max_reduce_kernel<<<1, 256, 0, stream>>>(p.cta_max, p.B * p.nblk, max_out);
+  launch_pdl(max_reduce_kernel, 1, 256, 0, stream, p.cta_max, p.B * p.nblk, max_out);
   return cudaGetLastError();
 }
 
@@ -420,12 +428,12 @@ cudaError_t launch_frontend_mfcc_finish(const FrontendParams& p, const MfccParam
     if (e != cudaSuccess) return e;
     once.set(smem2);
   }
-  mfcc_post_kernel<<<grid, 256, smem2, stream>>>(m);
+  launch_pdl(mfcc_post_kernel, grid, 256, smem2, stream, m);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int rows = 64;
   dim3 g2((p.T + rows - 1) / rows, p.B);
-  cmn_mask_kernel<<<g2, 128, 0, stream>>>(m.feats, m.partial, keep, p.T, m.K, p.nblk, rows);
+  launch_pdl(cmn_mask_kernel, g2, 128, 0, stream, m.feats, m.partial, keep, p.T, m.K, p.nblk, rows);
   return cudaGetLastError();
 }
 
@@ -434,7 +442,7 @@ cudaError_t launch_frontend_mfcc(const FrontendParams& p, const MfccParams& m, c
   cudaError_t e = ensure_frontend_smem(smem);
   if (e != cudaSuccess) return e;
   dim3 grid(p.nblk, p.B);
-  frontend_kernel<<<grid, 256, smem, stream>>>(p);
+  launch_pdl(frontend_kernel, grid, 256, smem, stream, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   return launch_frontend_mfcc_finish(p, m, keep, stream);     // clamps against all B*nblk per-CTA maxima (m.n_max)
@@ -445,12 +453,12 @@ cudaError_t launch_frontend(const FrontendParams& p, const int* keep, cudaStream
   cudaError_t e = ensure_frontend_smem(smem);
   if (e != cudaSuccess) return e;
   dim3 grid(p.nblk, p.B);
-  frontend_kernel<<<grid, 256, smem, stream>>>(p);
+  launch_pdl(frontend_kernel, grid, 256, smem, stream, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int rows = 64;
   dim3 g2((p.T + rows - 1) / rows, p.B);
-  cmn_mask_kernel<<<g2, 128, 0, stream>>>(p.feats, p.partial, keep, p.T, p.F, p.nblk, rows);
+  launch_pdl(cmn_mask_kernel, g2, 128, 0, stream, p.feats, p.partial, keep, p.T, p.F, p.nblk, rows);
   return cudaGetLastError();
 }
 

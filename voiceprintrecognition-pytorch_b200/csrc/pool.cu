@@ -12,6 +12,8 @@ namespace vpb {
 
 // grid (ceil(C/32), B), block 256 = 8 warps; lane = channel, warps stride over the R rows.
 __global__ void __launch_bounds__(256) colstats_kernel(const __grid_constant__ StatsParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                 // first access to mutable global memory comes after this
   __shared__ float red[8][33];
   __shared__ float bc[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -90,13 +92,15 @@ static bool pool_v2_enabled() {
 cudaError_t launch_colstats(const StatsParams& p, cudaStream_t stream) {
   if (pool_v2_enabled() && colstats_v2_supported(p)) return launch_colstats_v2(p, stream);
   dim3 grid((p.C + 31) / 32, p.B);
-  colstats_kernel<<<grid, 256, 0, stream>>>(p);
+  launch_pdl(colstats_kernel, grid, 256, 0, stream, p);
   return cudaGetLastError();
 }
 
 // Attentive statistics: alpha = softmax_t(logit[b, t, c]); mean = sum alpha x; std = sqrt(clamp(sum alpha (x-mean)^2, eps)).
 // x: src (in_ld/in_coff), logits: src2 (l_ld/l_coff); dst[b, c] = mean, dst[b, C + c] = std.
 __global__ void __launch_bounds__(256) asp_pool_kernel(const __grid_constant__ AspParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                 // first access to mutable global memory comes after this
   __shared__ float red[8][33];
   __shared__ float bc[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -150,6 +154,8 @@ __global__ void __launch_bounds__(256) asp_pool_kernel(const __grid_constant__ A
 // Same computation with the [T, 32-column] strips of x and logits staged ONCE in shared memory (each read from HBM once,
 // coalesced 128 B rows), then the three softmax / mean / variance sweeps run out of shared memory.
 __global__ void __launch_bounds__(256) asp_pool_smem_kernel(const __grid_constant__ AspParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                 // first access to mutable global memory comes after this
   extern __shared__ float sm[];
   __shared__ float red[8][33];
   __shared__ float bc[32];
@@ -240,15 +246,17 @@ cudaError_t launch_asp_pool(const AspParams& p, cudaStream_t stream) {
       if (e != cudaSuccess) return e;
       once.set(200 * 1024);
     }
-    asp_pool_smem_kernel<<<grid, 256, smem, stream>>>(p);
+    launch_pdl(asp_pool_smem_kernel, grid, 256, smem, stream, p);
     return cudaGetLastError();
   }
-  asp_pool_kernel<<<grid, 256, 0, stream>>>(p);
+  launch_pdl(asp_pool_kernel, grid, 256, 0, stream, p);
   return cudaGetLastError();
 }
 
 // Elementwise ops over [rows, C] (C % 4 == 0), float4 vectorised.
 __global__ void __launch_bounds__(256) ew_kernel(const __grid_constant__ EwParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                 // first access to mutable global memory comes after this
   const int c4n = p.C >> 2;
   const long long total = p.rows * c4n;
   float tmax = 0.f;
@@ -284,6 +292,8 @@ __global__ void __launch_bounds__(256) ew_kernel(const __grid_constant__ EwParam
 
 // dst[r, 0:C_out] = (x[r, 0:C], 0 ...): scalar, for feature dims that are not multiples of 4 (Spectrogram's n_fft/2+1 bins)
 __global__ void __launch_bounds__(256) pad_copy_kernel(const __grid_constant__ EwParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                 // first access to mutable global memory comes after this
   const long long total = p.rows * p.C_out;
   float tmax = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -300,14 +310,14 @@ cudaError_t launch_ew(const EwParams& p, cudaStream_t stream) {
   if (p.mode == VP_EW_PAD_COPY) {
     long long blocks = (p.rows * p.C_out + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    pad_copy_kernel<<<(int)(blocks < 1 ? 1 : blocks), 256, 0, stream>>>(p);
+    launch_pdl(pad_copy_kernel, (int)(blocks < 1 ? 1 : blocks), 256, 0, stream, p);
     return cudaGetLastError();
   }
   long long total = p.rows * (p.C >> 2);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
   if (blocks < 1) blocks = 1;
-  ew_kernel<<<(int)blocks, 256, 0, stream>>>(p);
+  launch_pdl(ew_kernel, (int)blocks, 256, 0, stream, p);
   return cudaGetLastError();
 }
 
@@ -315,6 +325,8 @@ cudaError_t launch_ew(const EwParams& p, cudaStream_t stream) {
 //   mode 0: nn.MaxPool2d(k, stride, padding)                      (res2net.py:105)
 //   mode 1: nn.AvgPool2d(k, stride, padding), count_include_pad   (res2net.py:33-34: divide by KT*KF always)
 __global__ void __launch_bounds__(256) pool2d_kernel(const __grid_constant__ PoolParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                 // first access to mutable global memory comes after this
   const int c4n = p.C >> 2;
   const long long total = (long long)p.B * p.Tout * p.Fout * c4n;
   float tmax = 0.f;
@@ -352,7 +364,7 @@ cudaError_t launch_pool2d(const PoolParams& p, cudaStream_t stream) {
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
   if (blocks < 1) blocks = 1;
-  pool2d_kernel<<<(int)blocks, 256, 0, stream>>>(p);
+  launch_pdl(pool2d_kernel, (int)blocks, 256, 0, stream, p);
   return cudaGetLastError();
 }
 

@@ -28,6 +28,8 @@ __device__ __forceinline__ void stage_strip(float* dst, const float* src, int ld
 }
 
 __global__ void __launch_bounds__(256) asp_pool_v2_kernel(const __grid_constant__ AspParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                 // first access to mutable global memory comes after this
   extern __shared__ __align__(16) float sm2[];
   __shared__ float red[8][33];
   __shared__ float bc[32];
@@ -96,13 +98,15 @@ cudaError_t launch_asp_pool_v2(const AspParams& p, cudaStream_t stream) {
     once.set(100 * 1024);
   }
   dim3 grid((p.C + 31) / 32, p.B);
-  asp_pool_v2_kernel<<<grid, 256, smem, stream>>>(p);
+  launch_pdl(asp_pool_v2_kernel, grid, 256, smem, stream, p);
   return cudaGetLastError();
 }
 
 // colstats for the modes whose whole [R, 32] strip fits in shared memory (1-D maps): one trip to HBM, then the same
 // two-pass mean / centred sum of squares as colstats_kernel, out of shared memory.
 __global__ void __launch_bounds__(256) colstats_v2_kernel(const __grid_constant__ StatsParams p) {
+  pdl_launch_dependents();
+  pdl_wait();                 // first access to mutable global memory comes after this
   extern __shared__ __align__(16) float sm2[];
   __shared__ float red[8][33];
   __shared__ float bc[32];
@@ -163,7 +167,7 @@ cudaError_t launch_colstats_v2(const StatsParams& p, cudaStream_t stream) {
     once.set(100 * 1024);
   }
   dim3 grid((p.C + 31) / 32, p.B);
-  colstats_v2_kernel<<<grid, 256, smem, stream>>>(p);
+  launch_pdl(colstats_v2_kernel, grid, 256, smem, stream, p);
   return cudaGetLastError();
 }
 
