@@ -178,13 +178,33 @@ def _sharded_worker(rank, world, port, backend, feature, same_gpu, out_dir):
 
 
 def _run_sharded(world, backend, feature, same_gpu):
+    """Sharded vs single-process result of the same list, on every rank.
+
+    * split-TF32 engine (VPB_TC_F16=0): BIT EXACT -- every op is per-utterance and shard-invariant (global Lmax padding,
+      MFCC's call-wide clamp maximum all-reduced), so sharding cannot change a single bit.
+    * default engine (two-term FP16 split): the power-of-two activation scale of a layer comes from the maximum over the
+      tensor the kernel sees -- the whole batch in one process, the shard under sharding.  A different power of two moves
+      the fp16 subnormal floor of the lo terms (relative 2^-38 of the tensor maximum), which can flip the last bit of an
+      fp32 accumulation: agreement to a few ulp (<= 2e-6 relative L2), not bit for bit."""
     import torch.multiprocessing as mp
-    with tempfile.TemporaryDirectory() as td:
-        mp.spawn(_sharded_worker, args=(world, _free_port(), backend, feature, same_gpu, td), nprocs=world, join=True)
-        for r in range(world):
-            full, got = np.load(os.path.join(td, f'rank{r}.npy'))
-            assert got.shape == (9, 192)
-            assert np.array_equal(full, got), (feature, r, np.abs(full - got).max())     # bit exact on every rank
+    for f16, tol in (('0', 0.0), ('1', 2e-6)):
+        old = os.environ.get('VPB_TC_F16')
+        os.environ['VPB_TC_F16'] = f16                  # read at library load in the spawned ranks
+        try:
+            with tempfile.TemporaryDirectory() as td:
+                mp.spawn(_sharded_worker, args=(world, _free_port(), backend, feature, same_gpu, td), nprocs=world, join=True)
+                for r in range(world):
+                    full, got = np.load(os.path.join(td, f'rank{r}.npy'))
+                    assert got.shape == (9, 192)
+                    if tol == 0.0:
+                        assert np.array_equal(full, got), (feature, r, np.abs(full - got).max())
+                    else:
+                        assert rel_l2(got, full).max() <= tol, (feature, r, rel_l2(got, full).max())
+        finally:
+            if old is None:
+                os.environ.pop('VPB_TC_F16', None)
+            else:
+                os.environ['VPB_TC_F16'] = old
 
 
 @pytest.mark.parametrize('feature', ['Fbank', 'MFCC'])

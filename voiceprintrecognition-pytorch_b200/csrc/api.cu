@@ -389,8 +389,8 @@ static int validate_op(vp_program* p, const vp_op& o, int i) {
         return fail(h, VP_ERR_INVALID, "op %d: unbiased std needs >= 2 rows", i);
       TRY(check_act_buf(p, "src", o.src, view_floats((long long)o.B * R, o.in_ld, o.in_coff, o.Cin), false, i));
       if (o.mode == VP_STATS_SEG_CONTEXT) {
-        if (o.seg_len < 1 || o.n_seg != (int)((R + o.seg_len - 1) / o.seg_len) || o.n_seg > 64)
-          return fail(h, VP_ERR_INVALID, "op %d: n_seg must be ceil(R/seg_len) <= 64", i);
+        if (o.seg_len < 1 || o.n_seg != (int)((R + o.seg_len - 1) / o.seg_len))
+          return fail(h, VP_ERR_INVALID, "op %d: n_seg must be ceil(R/seg_len)", i);
         TRY(check_act_buf(p, "dst", o.dst, view_floats((long long)o.B * o.n_seg, o.out_ld, o.out_coff, o.Cin), true, i));
       } else {
         const int cols = o.mode == VP_STATS_MEAN ? o.Cin : 2 * o.Cin;

@@ -287,7 +287,95 @@ __global__ void __launch_bounds__(256) conv_c1_kernel(const __grid_constant__ Co
   if (p.amax_out) amax_commit(p.amax_out, tmax);
 }
 
+// Wide variant for the usual stems (N = 16 / 32 / 64 output channels, plain bias -> act -> affine -> act2 epilogue): one
+// thread owns TWO output positions x ALL N channels.  The transposed weights [tap][N] sit in shared memory and are read
+// as broadcast float4s (one LDS.128 feeds 8 FMAs), every input sample is loaded once per position, and a thread writes
+// 2 x N contiguous floats, so a warp's stores cover 64 x N x 4 contiguous bytes.  ~13 instructions per output instead of
+// ~25 for the generic kernel above, whose one-thread-per-4-channels layout re-loads every sample N/4 times.
+template <int NQ>      // N / 4
+__global__ void __launch_bounds__(256) conv_c1_wide_kernel(const __grid_constant__ ConvParams p) {
+  pdl_launch_dependents();
+  __shared__ float4 ws[49 * NQ];         // [tap][NQ]
+  __shared__ float4 bs[NQ], ss[NQ], hs[NQ];
+  const int taps = p.KT * p.KF;
+  for (int i = threadIdx.x; i < taps * NQ; i += 256) {
+    const int k = i / NQ, q = i - k * NQ;
+    ws[i] = make_float4(__ldg(p.w + (size_t)(q * 4 + 0) * p.w_ld + k), __ldg(p.w + (size_t)(q * 4 + 1) * p.w_ld + k),
+                        __ldg(p.w + (size_t)(q * 4 + 2) * p.w_ld + k), __ldg(p.w + (size_t)(q * 4 + 3) * p.w_ld + k));
+  }
+  for (int q = threadIdx.x; q < NQ; q += 256) {
+    bs[q] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ss[q] = p.post_s ? __ldg(reinterpret_cast<const float4*>(p.post_s) + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+    hs[q] = p.post_s ? __ldg(reinterpret_cast<const float4*>(p.post_h) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  pdl_wait();                            // weights / bias are immutable; the feature map and the output are not
+  float tmax = 0.f;
+  const long long pairs = ((long long)p.M + 1) >> 1;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < pairs; idx += (long long)gridDim.x * blockDim.x) {
+    float4 acc[2][NQ];
+    RowInfo r[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      r[u] = decode_row(p, (int)(2 * idx + u));
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) acc[u][q] = bs[q];
+    }
+    for (int kt = 0; kt < p.KT; ++kt)
+      for (int kf = 0; kf < p.KF; ++kf) {
+        float x[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int ti = r[u].t0 + kt * p.dT, fi = r[u].f0 + kf * p.dF;
+          x[u] = 0.f;
+          if (r[u].valid && (unsigned)ti < (unsigned)p.Tin && (unsigned)fi < (unsigned)p.Fin)
+            x[u] = __ldg(p.src + ((size_t)r[u].base + (size_t)ti * p.Fin + fi) * p.in_ld + p.in_coff);
+        }
+        const float4* wk = ws + (kt * p.KF + kf) * NQ;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const float4 w = wk[q];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            acc[u][q].x = fmaf(x[u], w.x, acc[u][q].x); acc[u][q].y = fmaf(x[u], w.y, acc[u][q].y);
+            acc[u][q].z = fmaf(x[u], w.z, acc[u][q].z); acc[u][q].w = fmaf(x[u], w.w, acc[u][q].w);
+          }
+        }
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!r[u].valid) continue;
+      float4* o = reinterpret_cast<float4*>(p.dst + (size_t)(2 * idx + u) * p.out_ld + p.out_coff);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        float4 v = acc[u][q];
+        v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+        v.x = fmaf(v.x, ss[q].x, hs[q].x); v.y = fmaf(v.y, ss[q].y, hs[q].y);
+        v.z = fmaf(v.z, ss[q].z, hs[q].z); v.w = fmaf(v.w, ss[q].w, hs[q].w);
+        v.x = apply_act(v.x, p.act2); v.y = apply_act(v.y, p.act2); v.z = apply_act(v.z, p.act2); v.w = apply_act(v.w, p.act2);
+        o[q] = v;
+        tmax = amax4(tmax, v);
+      }
+    }
+  }
+  if (p.amax_out) amax_commit(p.amax_out, tmax);
+}
+
 cudaError_t launch_conv_c1(const ConvParams& p, cudaStream_t stream) {
+  // wide variant: N in {16, 32, 64}, <= 49 taps, epilogue = bias / act / affine / act2 only (what every stem uses)
+  const bool plain = !p.ubias && !p.gate && !p.res && !p.sum && (p.N == 16 || p.N == 32 || p.N == 64) && p.KT * p.KF <= 49 &&
+                     (p.out_ld & 3) == 0 && (p.out_coff & 3) == 0;
+  static int wide_pref = -1;
+  if (wide_pref < 0) { const char* e = getenv("VPB_C1_WIDE"); wide_pref = (e && e[0] == '0') ? 0 : 1; }
+  if (plain && wide_pref) {
+    const long long pairs = ((long long)p.M + 1) >> 1;
+    long long blocks = (pairs + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (p.N == 16) launch_pdl(conv_c1_wide_kernel<4>, (int)blocks, 256, 0, stream, p);
+    else if (p.N == 32) launch_pdl(conv_c1_wide_kernel<8>, (int)blocks, 256, 0, stream, p);
+    else launch_pdl(conv_c1_wide_kernel<16>, (int)blocks, 256, 0, stream, p);
+    return cudaGetLastError();
+  }
   long long total = (long long)p.M * (p.N >> 2);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;

@@ -478,9 +478,84 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     float descale = 1.f;                           // fp16 split: 2^-k of the weight image x 2^-s of the activation scale
     if constexpr (F16) descale = a.descale * exp2i(-f16_scale_exp(__ldg(p.amax_in)));
     float tmax = 0.f;                              // running max |y| of everything this thread stores (amax_out slot)
+    // Fast path (ncu, round 2: with 128 x 256 tiles the four epilogue warps, ~370 dependent instructions per 32-column
+    // chunk, were the pacing role -- the MMA warp spent its time waiting for tmem_empty).  The common epilogue shape
+    // -- bias, optional ReLU, optional BN affine, nothing per utterance, no residual -- on a tile without row / column
+    // tails needs no predicates, one pointer per thread and three FP instructions per element.
+    const bool simple = !p.ubias && !p.gate && !p.res && !p.sum && (p.act == VP_ACT_NONE || p.act == VP_ACT_RELU) &&
+                        p.act2 == VP_ACT_NONE;
+    const bool relu = p.act == VP_ACT_RELU;
+    const size_t row4 = (size_t)4 * p.out_ld;      // floats between the rows rsub + 4i and rsub + 4(i+1)
     for (int g = cluster_id; g < total_groups; g += n_clusters) {
       const int mbase = ((g / a.n_tiles) * (int)C + (int)crank) * BM + warp * 32;
       const int n0 = (g % a.n_tiles) * BN;
+      if (simple && mbase + 32 <= p.M && n0 + BN <= p.N) {
+        float* o0 = p.dst + (size_t)(mbase + rsub) * p.out_ld + p.out_coff + n0 + cg;
+        for (int ch = 0; ch + 1 < a.n_chunks; ++ch, ++ccount) {      // chunk folding exactly as in the general path
+          const int accf = ccount & 1;
+          mbar_wait(tfull0 + 8 * accf, (ccount >> 1) & 1);
+          tc_fence_after();
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + lane_base + (uint32_t)(accf * BN + c0), v);
+            if (ch > 0) {
+              float r[32];
+              tmem_ld32(tmem_base + lane_base + run_col + (uint32_t)c0, r);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += r[j];
+            }
+            tmem_st32(tmem_base + lane_base + run_col + (uint32_t)c0, v);
+          }
+          tc_fence_before();
+          mbar_arrive(tempty0 + 8 * accf);
+        }
+        const int acc = ccount & 1;
+        mbar_wait(tfull0 + 8 * acc, (ccount >> 1) & 1);
+        ++ccount;
+        tc_fence_after();
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          const int n = n0 + c0 + cg;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = b4;
+          if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          if (p.post_s) {
+            s4 = __ldg(reinterpret_cast<const float4*>(p.post_s + n));
+            h4 = __ldg(reinterpret_cast<const float4*>(p.post_h + n));
+          }
+          {
+            float v[32];
+            tmem_ld32(tmem_base + lane_base + (uint32_t)(acc * BN + c0), v);
+            if (a.n_chunks > 1) {
+              float r[32];
+              tmem_ld32(tmem_base + lane_base + run_col + (uint32_t)c0, r);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += r[j];
+            }
+            if (c0 + 32 >= BN) {
+              tc_fence_before();
+              mbar_arrive(tempty0 + 8 * acc);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pad_u32 + (uint32_t)(lane * 36 + j) * 4u), "f"(v[j]),
+                           "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
+                           : "memory");
+          }
+          __syncwarp();
+          float* o = o0 + c0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 x = *reinterpret_cast<const float4*>(pad + (rsub + 4 * i) * 36 + cg);
+            x.x = fmaf(x.x, descale, b4.x); x.y = fmaf(x.y, descale, b4.y);      // descale == 1 on the tf32 path
+            x.z = fmaf(x.z, descale, b4.z); x.w = fmaf(x.w, descale, b4.w);
+            if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            x.x = fmaf(x.x, s4.x, h4.x); x.y = fmaf(x.y, s4.y, h4.y); x.z = fmaf(x.z, s4.z, h4.z); x.w = fmaf(x.w, s4.w, h4.w);
+            *reinterpret_cast<float4*>(o + i * row4) = x;
+            tmax = amax4(tmax, x);
+          }
+          __syncwarp();
+        }
+        continue;
+      }
       // per-tile row state: output pointers, validity, per-utterance rows
       float* optr[8];
       int urow[8];
@@ -553,8 +628,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             v[i] = *reinterpret_cast<const float4*>(pad + (rsub + 4 * i) * 36 + cg);
-            if constexpr (F16) { v[i].x *= descale; v[i].y *= descale; v[i].z *= descale; v[i].w *= descale; }
-            v[i].x += b4.x; v[i].y += b4.y; v[i].z += b4.z; v[i].w += b4.w;
+            // acc * descale + bias in one rounding (descale == 1 on the tf32 path: exactly acc + bias) -- the same
+            // expression as the fast path above, so a row's result does not depend on which path its tile took
+            v[i].x = fmaf(v[i].x, descale, b4.x); v[i].y = fmaf(v[i].y, descale, b4.y);
+            v[i].z = fmaf(v[i].z, descale, b4.z); v[i].w = fmaf(v[i].w, descale, b4.w);
           }
           if (p.ubias) {
 #pragma unroll
@@ -643,8 +720,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
 // Host-visible tiling rule (mirrored by the Python packer mvector/engine.py::tc_tile_n).
 // Layers with K > 1536 are accumulated in chunks (see the MMA issuer) and need a third TMEM accumulator -> N tile <= 128.
-static const int KC_BLOCKS = 16;           // 512 K elements per accumulation chunk
-static bool tc_chunked(int K) { return K > 1536; }
+// VPB_TC_CHUNK_K / VPB_TC_KC (dev knobs, must be set identically for the Python packer): layers with K above the first are
+// accumulated in chunks of the second (a multiple of 64)
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+static int chunk_threshold() { static int v = env_int("VPB_TC_CHUNK_K", 1536); return v; }
+static int chunk_elems() { static int v = env_int("VPB_TC_KC", 512); return (v >= 64 && v % 64 == 0) ? v : 512; }
+static bool tc_chunked(int K) { return K > chunk_threshold(); }
 static int tc_tile_n(int N, int K) {
   if (N >= 256 && !tc_chunked(K)) return 256;
   if (N >= 128) return 128;
@@ -687,13 +768,20 @@ static cudaError_t launch_conv_tc_impl(const ConvParams& p, const float* w_img, 
   a.BN = p.tc_bn;
   const int bke = f16 ? 64 : BK;
   const int stage_bytes = 2 * A_TILE + 2 * a.BN * 128;
-  a.stages = SMEM_BUDGET / stage_bytes;
+  // Multi-tap convs on narrow tiles re-read every input element KT*KF times and are gather-, not tensor-bound: a smaller
+  // pipeline leaves the rest of the 228 KB to the L1, which then serves the repeated taps instead of the L2
+  // (VPB_TC_NARROW_KB: shared-memory budget in KB for those layers; measured in profiles/r2_narrow_l1.md).
+  static int narrow_kb = -1;
+  if (narrow_kb < 0) { const char* ev = getenv("VPB_TC_NARROW_KB"); narrow_kb = ev ? atoi(ev) : 200; if (narrow_kb < 64 || narrow_kb > 200) narrow_kb = 200; }
+  const int budget = (p.KT * p.KF > 1 && a.BN <= 64) ? narrow_kb * 1024 : SMEM_BUDGET;
+  a.stages = budget / stage_bytes;
   if (a.stages > 8) a.stages = 8;
-  if (a.stages < 2) return cudaErrorInvalidConfiguration;
+  if (a.stages < 2) a.stages = 2;
+  if (a.stages * stage_bytes > SMEM_BUDGET) return cudaErrorInvalidConfiguration;
   a.m_tiles = (p.M + BM - 1) / BM;
   a.n_tiles = (p.N + a.BN - 1) / a.BN;
   a.k_blocks = (p.K + bke - 1) / bke;
-  a.kc = tc_chunked(p.K) ? KC_BLOCKS * BK / bke : a.k_blocks;      // chunks of 512 K elements either way
+  a.kc = tc_chunked(p.K) ? chunk_elems() / bke : a.k_blocks;       // chunks of 512 K elements either way
   a.n_chunks = (a.k_blocks + a.kc - 1) / a.kc;
   // accumulator regions [acc*BN, +BN) (+ running sum at 2*BN when chunked); tcgen05.ld reads 32 columns at a time, so
   // the last 32-column read of the last region must stay inside the allocation

@@ -38,6 +38,22 @@ __global__ void __launch_bounds__(256) colstats_kernel(const __grid_constant__ S
   if (p.mode == VP_STATS_SEG_CONTEXT) {
     // context[b, s, c] = mean_T(x) + mean over segment s (last segment divides by its in-bounds length)
     __shared__ float segsum[64][32];
+    if (p.n_seg > 64) {
+      // very long audio (> 64 segments = 128 s at CAM++'s 100-frame segments after the stride-2 TDNN): two sweeps -- the
+      // utterance total first, then one segment at a time -- instead of parking the segment sums in shared memory
+      float v = 0.f;
+      if (ok) for (int r = wid; r < p.R; r += 8) v += x[(size_t)r * p.in_ld];
+      const float mean = block_sum(v) / (float)p.R;
+      for (int s = 0; s < p.n_seg; ++s) {
+        const int r0 = s * p.seg_len, r1 = min(r0 + p.seg_len, p.R);
+        float u = 0.f;
+        if (ok) for (int r = r0 + wid; r < r1; r += 8) u += x[(size_t)r * p.in_ld];
+        __syncthreads();
+        const float ss = block_sum(u);
+        if (wid == 0 && ok) p.dst[((size_t)b * p.n_seg + s) * p.out_ld + p.out_coff + c] = mean + ss / (float)(r1 - r0);
+      }
+      return;
+    }
     float total = 0.f;
     for (int s = 0; s < p.n_seg; ++s) {
       const int r0 = s * p.seg_len, r1 = min(r0 + p.seg_len, p.R);

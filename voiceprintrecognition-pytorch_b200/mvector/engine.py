@@ -63,7 +63,7 @@ class Engine:
 
     def close(self):
         if self._h:
-            for p in self._programs:
+            for p in list(self._programs):
                 p.close()
             L.lib().vp_destroy(self._h)
             self._h = C.c_void_p()
@@ -116,7 +116,7 @@ class WeightArena:
 def tc_tile_n(N, K=0):
     """N tile of the tcgen05 engine (must match conv_tc.cu::tc_tile_n): 256-wide tiles, except for long-K layers
     (K > 1536) whose chunked accumulation keeps a third TMEM accumulator and therefore uses 128-wide tiles."""
-    if N >= 256 and K <= 1536:
+    if N >= 256 and K <= int(os.environ.get('VPB_TC_CHUNK_K', '1536')):
         return 256
     if N >= 128:
         return 128
@@ -506,3 +506,7 @@ class Program:
         if self._p:
             L.lib().vp_program_destroy(self._p)
             self._p = C.c_void_p()
+            try:
+                self.engine._programs.remove(self)       # a long-lived server must not accumulate closed programs
+            except ValueError:
+                pass

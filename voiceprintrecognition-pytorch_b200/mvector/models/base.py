@@ -41,7 +41,7 @@ class Backbone:
         self._programs = OrderedDict()
         self._off = {}
         self.engine_pref = L.ENGINE_AUTO
-        self.max_cached_programs = 8
+        self.max_cached_programs = 64      # programs are host-side op lists: the workspace is the handle's shared arena
         self.training = False
         self._blob = None
         self._uploaded = False

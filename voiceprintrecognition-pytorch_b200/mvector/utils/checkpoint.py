@@ -15,7 +15,14 @@ def load_pretrained(model, pretrained_model, use_gpu=True):
     assert os.path.exists(pretrained_model), f"{pretrained_model} 模型不存在！"
     try:
         state = torch.load(pretrained_model, map_location='cpu', weights_only=True)
-    except Exception:  # checkpoints pickled with non-tensor payloads (the reference loads with weights_only=False)
+    except Exception as e:
+        # Checkpoints pickled with non-tensor payloads need the unrestricted unpickler, which executes code from the file.
+        # The reference always loads that way (checkpoint.py:29, torch.load default of its torch pin); here it is an
+        # explicit opt-in so that a drop-in never runs a pickle payload silently.
+        if os.environ.get('VPB_ALLOW_UNSAFE_PICKLE') != '1':
+            raise RuntimeError(f'{pretrained_model} is not a plain tensor state_dict ({type(e).__name__}: {e}); set '
+                               'VPB_ALLOW_UNSAFE_PICKLE=1 to load it with the unrestricted pickle loader') from e
+        logger.warning(f'{pretrained_model}: falling back to torch.load(weights_only=False) (VPB_ALLOW_UNSAFE_PICKLE=1)')
         state = torch.load(pretrained_model, map_location='cpu', weights_only=False)
     shapes = model.param_shapes()
     for name in list(state.keys()):
