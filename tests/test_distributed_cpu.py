@@ -52,7 +52,8 @@ class _FakePredictor:
 
     def __init__(self):
         from mvector.utils.utils import dict_to_object
-        self.configs = dict_to_object({'dataset_conf': {'dataset': {'sample_rate': 16000, 'min_duration': 0.001}}})
+        self.configs = dict_to_object({'dataset_conf': {'dataset': {'sample_rate': 16000, 'min_duration': 0.001,
+                                                                    'use_dB_normalization': False}}})
         self.loaded = []
 
     def _load_audio(self, audio_data, sample_rate=16000):
@@ -75,12 +76,17 @@ def _worker_predict(rank, world, port, n):
     dist.init_process_group('gloo', rank=rank, world_size=world)
     rng = np.random.default_rng(1)
     waves = [rng.standard_normal(int(rng.integers(50, 400))).astype(np.float32) for _ in range(n)]
+    x, ratio = pad_to_global_max(waves)
+    lo, hi = shard_range(n, rank, world)
+    # float64 arrays need _load_audio's conversion: a rank decodes only its own shard, the rest contributes lengths
+    pred = _FakePredictor()
+    got = predict_batch_sharded(pred, [w.astype(np.float64) for w in waves], as_numpy=False)
+    assert torch.equal(got, _fake_embed(x, ratio))               # global Lmax / ratios although only the shard was staged
+    assert sorted(pred.loaded) == sorted(len(w) for w in waves[lo:hi])
+    # raw float32 arrays at the model's rate (dB normalisation off) are used in place: nothing is decoded at all
     pred = _FakePredictor()
     got = predict_batch_sharded(pred, waves, as_numpy=False)
-    x, ratio = pad_to_global_max(waves)
-    assert torch.equal(got, _fake_embed(x, ratio))               # global Lmax / ratios although only the shard was staged
-    lo, hi = shard_range(n, rank, world)
-    assert sorted(pred.loaded) == sorted(len(w) for w in waves[lo:hi])     # a rank decodes only its own shard
+    assert torch.equal(got, _fake_embed(x, ratio)) and pred.loaded == []
     dist.barrier()
     dist.destroy_process_group()
 

@@ -159,13 +159,19 @@ def predict_batch_sharded(predictor, audios_data, sample_rate=16000, group=None,
     n = len(audios_data)
     target_sr = predictor.configs.dataset_conf.dataset.sample_rate
     lo, hi = shard_range(n, rank, world)
+    ds = predictor.configs.dataset_conf.dataset
     lens, mine = [], {}
+    raw = sample_rate == target_sr and not ds.get('use_dB_normalization', False)
     for i, a in enumerate(audios_data):
-        if isinstance(a, np.ndarray) and a.ndim == 1 and sample_rate == target_sr and not (lo <= i < hi):
-            # length is all the other ranks' items contribute (Lmax); decoding / resampling changes nothing for raw arrays
-            min_dur = predictor.configs.dataset_conf.dataset.min_duration
-            assert a.shape[0] / float(sample_rate) >= min_dur, f'音频太短，最小应该为{min_dur}s，当前音频为{a.shape[0] / float(sample_rate)}s'
+        if type(a) is np.ndarray and a.ndim == 1 and (not (lo <= i < hi) or (raw and a.dtype == np.float32 and a.flags.c_contiguous)) \
+                and sample_rate == target_sr:
+            # a raw mono array at the model's rate: its length is all Lmax needs from the other ranks' items, and this
+            # rank's own items are used in place when _load_audio would hand them back unchanged (predict.py:196-211)
+            assert a.shape[0] / float(sample_rate) >= ds.min_duration, \
+                f'音频太短，最小应该为{ds.min_duration}s，当前音频为{a.shape[0] / float(sample_rate)}s'
             lens.append(a.shape[0])
+            if lo <= i < hi:
+                mine[i] = a
             continue
         seg = predictor._load_audio(audio_data=a, sample_rate=sample_rate)
         lens.append(seg.samples.shape[0])

@@ -61,6 +61,7 @@ class MVectorPredictor:
         self._pinned = None
         self._copy_stream = None
         self._ws_per_utt = {}
+        self._trace = None
 
         self.speaker_diarize = SpeakerDiarization()
         # similarity matrix of the spectral clustering (speaker_diarization.py:254-257) on the device
@@ -230,6 +231,10 @@ class MVectorPredictor:
         chunk (<= MAX_BATCH utterances) are complete the main stream runs its program.  One D2H of the result at the end."""
         from . import _lib as L
         import ctypes as C
+        import time
+        tr = self._trace                                 # None, or a list the caller wants (label, perf_counter) pairs in
+        mark = (lambda label: tr.append((label, time.perf_counter()))) if tr is not None else (lambda label: None)
+        mark('embed_waves:start')
         B = len(waves)
         fz = self._audio_featurizer
         D = self.predictor.embd_dim
@@ -263,6 +268,7 @@ class MVectorPredictor:
         ptrs = np.fromiter((w.__array_interface__['data'][0] for w in waves), dtype=np.uint64, count=B)
         lens = np.fromiter((w.shape[0] for w in waves), dtype=np.int32, count=B)
         nthreads = self._gather_threads()
+        mark('host prep done (keep, buffers, pointer table)')
         fe_fn = lib.vp_fbank if desc.kind == 0 else (lib.vp_mfcc if desc.post == 1 else lib.vp_melspec)
         free_ev = [None, None]                          # front-end finished reading device slot / pinned slot reusable
         next_chunk = 0
@@ -278,6 +284,7 @@ class MVectorPredictor:
                                        C.c_void_p(host.data_ptr()), C.c_void_p(dw.data_ptr()), self.COPY_SLICE, nthreads, cs_ptr)
             if rc != L.VP_OK:
                 raise L.VpError(rc, 'vp_host_stage_h2d failed')
+            mark(f'stage {gi}: {n} utterances gathered, H2D enqueued')
             kp = C.c_void_p(keep_all.data_ptr() + 4 * g0) if keep_all is not None else C.c_void_p()
             if whole and group is not None:
                 fz.mfcc_sharded(dw, n, lmax, kp, feats, scratch, cs, group)
@@ -296,7 +303,10 @@ class MVectorPredictor:
                 next_chunk = hi
         # the staging / feature buffers go back to the allocator for the main stream: order the copy stream before that
         main.wait_stream(cs)
-        return emb.cpu().numpy() if to_numpy else emb
+        mark('all kernels enqueued')
+        out = emb.cpu().numpy() if to_numpy else emb
+        mark('result on host' if to_numpy else 'returned device tensor')
+        return out
 
     def embed_device(self, wave_dev, lens=None, lmax=None, keep=None, group=None):
         """Device-resident twin of ``predict_batch``'s compute half: ``wave_dev`` is a CUDA float32 ``[B, Lmax]`` matrix,
@@ -340,10 +350,24 @@ class MVectorPredictor:
 
     def predict_batch(self, audios_data, sample_rate=16000, batch_size=32):
         """预测一批音频的特征 (predict.py:231-265) -> np.ndarray [B, embd_dim], order preserved."""
-        waves = [np.ascontiguousarray(self._load_audio(audio_data=a, sample_rate=sample_rate).samples, dtype=np.float32)
-                 for a in audios_data]
+        waves = self._load_batch(audios_data, sample_rate)
         lmax = max(w.shape[0] for w in waves)
         return self._embed_waves(waves, lmax, masked=True)
+
+    def _load_batch(self, audios_data, sample_rate=16000):
+        """predict.py:244-247 for a list: every item through ``_load_audio``.  Raw float32 mono arrays that are already at
+        the model's sample rate, with dB normalisation off, come out of ``_load_audio`` unchanged (predict.py:196-211:
+        from_ndarray, duration assert, no resample, no normalise) -- they are checked in one pass and used in place instead
+        of being wrapped and re-wrapped one by one (a 256-utterance batch spends more time in that loop than the GPU in
+        its front-end)."""
+        ds = self.configs.dataset_conf.dataset
+        if sample_rate == ds.sample_rate and not ds.use_dB_normalization and all(
+                type(a) is np.ndarray and a.dtype == np.float32 and a.ndim == 1 and a.flags.c_contiguous for a in audios_data):
+            shortest = min(a.shape[0] for a in audios_data) if len(audios_data) else 0
+            if len(audios_data) == 0 or shortest / float(sample_rate) >= ds.min_duration:
+                return list(audios_data)
+        return [np.ascontiguousarray(self._load_audio(audio_data=a, sample_rate=sample_rate).samples, dtype=np.float32)
+                for a in audios_data]
 
     def contrast(self, audio_data1, audio_data2):
         """声纹对比 (predict.py:267-279) -> cosine similarity"""
