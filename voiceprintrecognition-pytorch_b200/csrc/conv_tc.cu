@@ -130,6 +130,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __noinline__ float4 act4_slow(float4 v, int act) {
+  v.x = apply_act(v.x, act); v.y = apply_act(v.y, act); v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
+  return v;
+}
+
 template <int MODE> struct Slot;
 template <> struct Slot<0> { float4 v[ROWS_PER_THREAD]; };
 template <> struct Slot<1> { float4 v[ROWS_PER_THREAD]; float4 u[ROWS_PER_THREAD]; };
@@ -469,9 +474,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const int cg = (lane & 7) * 4;           // this thread's 4 columns inside the chunk
     const int rsub = lane >> 3;              // rows rsub + 4*i
     const bool need_urow = (p.gate != nullptr) || (p.ubias != nullptr);
-    auto act4 = [](float4& v, int act) {     // called under a warp-uniform branch: one switch per float4, not per element
-      v.x = apply_act(v.x, act); v.y = apply_act(v.y, act); v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
-    };
+    // The transcendental activations (tanh / sigmoid / SiLU / hardtanh) live in ONE out-of-line function: inlined they
+    // were ~100 instructions per element x 32 elements x 2 call sites = more than half of the kernel's 11 k SASS
+    // instructions, and ncu showed `stall_no_instruction` (instruction-cache misses) at 1.4 per issued instruction.
     uint32_t ccount = 0;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const uint32_t run_col = (uint32_t)(2 * BN);   // running-sum accumulator (only when n_chunks > 1)
@@ -482,15 +487,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     // chunk, were the pacing role -- the MMA warp spent its time waiting for tmem_empty).  The common epilogue shape
     // -- bias, optional ReLU, optional BN affine, nothing per utterance, no residual -- on a tile without row / column
     // tails needs no predicates, one pointer per thread and three FP instructions per element.
-    const bool simple = !p.ubias && !p.gate && !p.res && !p.sum && (p.act == VP_ACT_NONE || p.act == VP_ACT_RELU) &&
-                        p.act2 == VP_ACT_NONE;
-    const bool relu = p.act == VP_ACT_RELU;
+    const bool simple = !p.ubias && !p.gate && !p.sum && (p.act == VP_ACT_NONE || p.act == VP_ACT_RELU) &&
+                        (p.act2 == VP_ACT_NONE || p.act2 == VP_ACT_RELU);
+    const bool relu = p.act == VP_ACT_RELU, relu2 = p.act2 == VP_ACT_RELU;
     const size_t row4 = (size_t)4 * p.out_ld;      // floats between the rows rsub + 4i and rsub + 4(i+1)
+    const size_t res4 = (size_t)4 * p.res_ld;
     for (int g = cluster_id; g < total_groups; g += n_clusters) {
       const int mbase = ((g / a.n_tiles) * (int)C + (int)crank) * BM + warp * 32;
       const int n0 = (g % a.n_tiles) * BN;
       if (simple && mbase + 32 <= p.M && n0 + BN <= p.N) {
         float* o0 = p.dst + (size_t)(mbase + rsub) * p.out_ld + p.out_coff + n0 + cg;
+        const float* r0 = p.res ? p.res + (size_t)(mbase + rsub) * p.res_ld + p.res_coff + n0 + cg : nullptr;
         for (int ch = 0; ch + 1 < a.n_chunks; ++ch, ++ccount) {      // chunk folding exactly as in the general path
           const int accf = ccount & 1;
           mbar_wait(tfull0 + 8 * accf, (ccount >> 1) & 1);
@@ -542,13 +549,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           }
           __syncwarp();
           float* o = o0 + c0;
+          float4 rr[8];
+          if (r0) {                                 // residual: all eight loads in flight before the first use
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rr[i] = __ldg(reinterpret_cast<const float4*>(r0 + c0 + i * res4));
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4 x = *reinterpret_cast<const float4*>(pad + (rsub + 4 * i) * 36 + cg);
             x.x = fmaf(x.x, descale, b4.x); x.y = fmaf(x.y, descale, b4.y);      // descale == 1 on the tf32 path
             x.z = fmaf(x.z, descale, b4.z); x.w = fmaf(x.w, descale, b4.w);
             if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-            x.x = fmaf(x.x, s4.x, h4.x); x.y = fmaf(x.y, s4.y, h4.y); x.z = fmaf(x.z, s4.z, h4.z); x.w = fmaf(x.w, s4.w, h4.w);
+            if (p.post_s) {
+              x.x = fmaf(x.x, s4.x, h4.x); x.y = fmaf(x.y, s4.y, h4.y); x.z = fmaf(x.z, s4.z, h4.z); x.w = fmaf(x.w, s4.w, h4.w);
+            }
+            if (r0) { x.x += rr[i].x; x.y += rr[i].y; x.z += rr[i].z; x.w += rr[i].w; }
+            if (relu2) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
             *reinterpret_cast<float4*>(o + i * row4) = x;
             tmax = amax4(tmax, x);
           }
@@ -556,18 +572,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
         continue;
       }
-      // per-tile row state: output pointers, validity, per-utterance rows
-      float* optr[8];
-      int urow[8];
+      // per-tile row validity (rows rsub + 4i of this warp's 32)
       uint32_t rowok = 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = mbase + rsub + 4 * i;
-        const bool ok = m < p.M;
-        rowok |= ok ? (1u << i) : 0u;
-        optr[i] = p.dst + (size_t)(ok ? m : 0) * p.out_ld + p.out_coff + n0 + cg;
-        urow[i] = (need_urow && ok) ? urow_of(p, m) : 0;
-      }
+      for (int i = 0; i < 8; ++i) rowok |= (mbase + rsub + 4 * i < p.M) ? (1u << i) : 0u;
       // fold all but the last accumulation chunk into the running sum (TMEM columns [2BN, 3BN))
       for (int ch = 0; ch + 1 < a.n_chunks; ++ch, ++ccount) {
         const int accf = ccount & 1;
@@ -624,81 +632,46 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
         __syncwarp();
         if (nok) {
-          float4 v[8];
-#pragma unroll
+          // General epilogue, one row at a time (deliberately NOT unrolled: this path serves the tile tails and the
+          // per-utterance / gated / accumulate-into layers; the hot shapes take the fast path above, and keeping this
+          // one compact keeps the kernel's instruction footprint -- and its instruction-cache misses -- down).
+#pragma unroll 1
           for (int i = 0; i < 8; ++i) {
-            v[i] = *reinterpret_cast<const float4*>(pad + (rsub + 4 * i) * 36 + cg);
+            if (!(rowok & (1u << i))) continue;
+            const int m = mbase + rsub + 4 * i;
+            float4 x = *reinterpret_cast<const float4*>(pad + (rsub + 4 * i) * 36 + cg);
             // acc * descale + bias in one rounding (descale == 1 on the tf32 path: exactly acc + bias) -- the same
-            // expression as the fast path above, so a row's result does not depend on which path its tile took
-            v[i].x = fmaf(v[i].x, descale, b4.x); v[i].y = fmaf(v[i].y, descale, b4.y);
-            v[i].z = fmaf(v[i].z, descale, b4.z); v[i].w = fmaf(v[i].w, descale, b4.w);
-          }
-          if (p.ubias) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 u = __ldg(reinterpret_cast<const float4*>(p.ubias + (size_t)urow[i] * p.N + n));
-              v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
+            // expression as the fast path, so a row's result does not depend on which path its tile took
+            x.x = fmaf(x.x, descale, b4.x); x.y = fmaf(x.y, descale, b4.y);
+            x.z = fmaf(x.z, descale, b4.z); x.w = fmaf(x.w, descale, b4.w);
+            const int ur = need_urow ? urow_of(p, m) : 0;
+            if (p.ubias) {
+              const float4 u = __ldg(reinterpret_cast<const float4*>(p.ubias + (size_t)ur * p.N + n));
+              x.x += u.x; x.y += u.y; x.z += u.z; x.w += u.w;
             }
-          }
-          if (p.act == VP_ACT_RELU) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f); }
-          } else if (p.act != VP_ACT_NONE) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) act4(v[i], p.act);
-          }
-          if (p.post_s) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              v[i].x = fmaf(v[i].x, s4.x, h4.x); v[i].y = fmaf(v[i].y, s4.y, h4.y);
-              v[i].z = fmaf(v[i].z, s4.z, h4.z); v[i].w = fmaf(v[i].w, s4.w, h4.w);
+            if (p.act == VP_ACT_RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            else if (p.act != VP_ACT_NONE) x = act4_slow(x, p.act);
+            if (p.post_s) {
+              x.x = fmaf(x.x, s4.x, h4.x); x.y = fmaf(x.y, s4.y, h4.y); x.z = fmaf(x.z, s4.z, h4.z); x.w = fmaf(x.w, s4.w, h4.w);
             }
-          }
-          if (p.gate) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 gt = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)urow[i] * p.N + n));
-              v[i].x *= gt.x; v[i].y *= gt.y; v[i].z *= gt.z; v[i].w *= gt.w;
+            if (p.gate) {
+              const float4 gt = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)ur * p.N + n));
+              x.x *= gt.x; x.y *= gt.y; x.z *= gt.z; x.w *= gt.w;
             }
-          }
-          if (p.res) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (rowok & (1u << i)) {
-                const float4 r = __ldg(reinterpret_cast<const float4*>(p.res + (size_t)(mbase + rsub + 4 * i) * p.res_ld + p.res_coff + n));
-                v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
-              }
+            if (p.res) {
+              const float4 r = __ldg(reinterpret_cast<const float4*>(p.res + (size_t)m * p.res_ld + p.res_coff + n));
+              x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
             }
-          }
-          if (p.act2 == VP_ACT_RELU) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f); }
-          } else if (p.act2 != VP_ACT_NONE) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) act4(v[i], p.act2);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (rowok & (1u << i)) {
-              *reinterpret_cast<float4*>(optr[i] + c0) = v[i];
-              tmax = amax4(tmax, v[i]);
+            if (p.act2 == VP_ACT_RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            else if (p.act2 != VP_ACT_NONE) x = act4_slow(x, p.act2);
+            *reinterpret_cast<float4*>(p.dst + (size_t)m * p.out_ld + p.out_coff + n) = x;
+            tmax = amax4(tmax, x);
+            if (p.sum) {                         // accumulate-into view (Res2 chains): sum[m, n] += y[m, n]
+              float4* q = reinterpret_cast<float4*>(p.sum + (size_t)m * p.sum_ld + p.sum_coff + n);
+              float4 sv = *q;
+              sv.x += x.x; sv.y += x.y; sv.z += x.z; sv.w += x.w;
+              *q = sv;
             }
-          if (p.sum) {                         // accumulate-into view (Res2 chains): sum[m, n] += y[m, n]
-            // all eight loads first, then the adds and stores: written as load-add-store per row the possible aliasing
-            // between rows forces the compiler to serialise eight global round trips per chunk
-            float4 sv[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              sv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (rowok & (1u << i))
-                sv[i] = *reinterpret_cast<const float4*>(p.sum + (size_t)(mbase + rsub + 4 * i) * p.sum_ld + p.sum_coff + n);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (rowok & (1u << i)) {
-                sv[i].x += v[i].x; sv[i].y += v[i].y; sv[i].z += v[i].z; sv[i].w += v[i].w;
-                *reinterpret_cast<float4*>(p.sum + (size_t)(mbase + rsub + 4 * i) * p.sum_ld + p.sum_coff + n) = sv[i];
-              }
           }
         }
         __syncwarp();
