@@ -422,12 +422,6 @@ def run_gpu_arm(args, cfg):
             with open(args.dump_ops, 'w') as f:
                 json.dump(acc, f, indent=0)
         conv = [a for a in acc if a['kind'] == L.OP_CONV and a['K'] > 0]
-        # dominant kernel = the (M, N, K, engine) class with the largest total device time in the step
-        classes = {}
-        for a in conv:
-            classes.setdefault((a['M'], a['N'], a['K'], a['engine']), []).append(a['ms'])
-        (tM, tN, tK, teng), tms = max(classes.items(), key=lambda kv: sum(kv[1]))
-        top_ms = sum(tms) / len(tms)
         peaks = {}
         ppath = os.path.join(ROOT, 'MEASURED_PEAKS.json')
         if os.path.exists(ppath):
@@ -436,25 +430,69 @@ def run_gpu_arm(args, cfg):
         peak = peaks.get('bf16_tflops')
         peak_src = 'MEASURED_PEAKS.json bf16_tflops (burst: the kernel is event-timed alone; of measured)'
         peak_sus = peaks.get('bf16_tflops_sustained')
+        hbm = peaks.get('hbm_gbs')
         if peak is None:
-            peak, peak_src, peak_sus = 1590.0, 'fallback 1.59 PFLOP/s burst (B200_PROFILING.md; of fallback)', 1400.0
-        achieved = 2.0 * tM * tN * tK / (top_ms * 1e-3) / 1e12
+            peak, peak_src, peak_sus, hbm = 1590.0, 'fallback 1.59 PFLOP/s burst (B200_PROFILING.md; of fallback)', 1400.0, 6650.0
+        # algorithmic work of every op from the lowered program (same op order as the profile): FLOPs = 2 M N K of the
+        # reference's conv / linear, bytes = every operand read once + the result written once
+        geo = pred.predictor.lower(cb, T0).finalize().ops
+        assert len(geo) == len(acc)
+        for a, o in zip(acc, geo):
+            rows_in, rows_out = o.B * o.Tin * o.Fin, o.B * o.Tout * o.Fout
+            if a['kind'] in (L.OP_CONV, L.OP_CONV_C1):
+                cin2 = o.Cin2 if o.src2_mode == L.SRC2_CONCAT else (o.Cin if o.src2_mode == L.SRC2_ADD else 0)
+                a['flops'] = 2.0 * a['M'] * a['N'] * a['K']
+                a['bytes'] = 4.0 * (rows_in * (o.Cin + cin2) + rows_out * o.Cout * (2 if o.res >= 0 else 1) + o.Cout * a['K'])
+            else:
+                a['flops'] = 0.0
+                reads = {L.OP_EW: 1 + (1 if o.res >= 0 else 0) + (1 if o.mode == L.EW_AFF else 0), L.OP_COLSTATS: 1,
+                         L.OP_ASP_POOL: 2, L.OP_POOL2D: 1}.get(a['kind'], 1)
+                writes = rows_in * o.Cin if a['kind'] == L.OP_EW else (rows_out * o.Cin if a['kind'] == L.OP_POOL2D else 0)
+                a['bytes'] = 4.0 * (reads * rows_in * o.Cin + writes)
+            a['t_tensor_ms'] = a['flops'] / (peak * 1e12) * 1e3
+            a['t_hbm_ms'] = a['bytes'] / (hbm * 1e9) * 1e3
+        classes = {}
+        for a in acc:
+            classes.setdefault((a['kind'], a['M'], a['N'], a['K'], a['engine']), []).append(a)
+        eng_name = {L.ENGINE_TC: 'conv_tc_kernel (tcgen05, split-TF32)', L.ENGINE_TC16: 'conv_tc_kernel (tcgen05, two-term FP16 split)',
+                    L.ENGINE_FFMA: 'conv_ffma / linear_small_m (fp32 FFMA)'}
+        kind_name = {L.OP_CONV: None, L.OP_CONV_C1: 'conv_c1 (Cin = 1 stem)', L.OP_COLSTATS: 'colstats', L.OP_ASP_POOL: 'asp_pool',
+                     L.OP_EW: 'ew', L.OP_POOL2D: 'pool2d'}
+
+        def describe(key, ops):
+            kind, M, N, K, eng = key
+            ms = sum(o_['ms'] for o_ in ops) / len(ops)
+            tt, th = ops[0]['t_tensor_ms'], ops[0]['t_hbm_ms']
+            bound = 'tensor' if tt >= th else 'hbm'
+            d = {'kernel': (kind_name.get(kind) or eng_name.get(eng, str(eng))) + f' M={M} N={N}' + (f' K={K}' if K else ''),
+                 'launches_per_forward': len(ops), 'ms_per_launch': ms, 'share_of_backbone': sum(o_['ms'] for o_ in ops) / total,
+                 'bound': bound, 'frac': max(tt, th) / ms}
+            if bound == 'tensor':
+                d.update(achieved=ops[0]['flops'] / (ms * 1e-3) / 1e12, peak=peak, unit='TFLOP/s')
+            else:
+                d.update(achieved=ops[0]['bytes'] / (ms * 1e-3) / 1e9, peak=hbm, unit='GB/s')
+            return d
+
+        by_time = sorted(classes.items(), key=lambda kv: -sum(o_['ms'] for o_ in kv[1]))
+        # the dominant kernel = the single launch with the largest device time; its class mates share shape and kernel
+        top_key = max(classes, key=lambda k: max(o_['ms'] for o_ in classes[k]))
+        top = describe(top_key, classes[top_key])
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
         if os.path.exists(tpath):
             with open(tpath) as f:
                 tj = json.load(f)
-            traffic = tj.get(f'{tM}x{tN}x{tK}')
+            traffic = tj.get(f'{top_key[1]}x{top_key[2]}x{top_key[3]}')
             traffic_src = tj.get('source', 'profiles/ (ncu --set full capture of the same kernel and shape; not measured in this run)')
         gemm_ms = sum(a['ms'] for a in conv)
-        gemm_flops = sum(2.0 * a['M'] * a['N'] * a['K'] for a in conv)
-        eng_name = {L.ENGINE_TC: 'conv_tc_kernel (tcgen05, split-TF32)', L.ENGINE_TC16: 'conv_tc_kernel (tcgen05, two-term FP16 split)',
-                    L.ENGINE_FFMA: 'conv_ffma_kernel (fp32 FFMA)'}.get(teng, str(teng))
+        gemm_flops = sum(a['flops'] for a in conv)
         step_flops = gemm_flops * n_chunks * world
-        roof = {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-                'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
-                'kernel': f'{eng_name} M={tM} N={tN} K={tK} x{len(tms)} per forward',
-                'kernel_ms': top_ms, 'kernel_share_of_backbone': sum(tms) / total,
+        roof = {'bound': top['bound'], 'achieved': top['achieved'], 'peak': top['peak'], 'unit': top['unit'], 'frac': top['frac'],
+                'traffic': traffic, 'traffic_source': traffic_src,
+                'peak_source': peak_src if top['bound'] == 'tensor' else 'MEASURED_PEAKS.json hbm_gbs (of measured)',
+                'kernel': top['kernel'] + f" x{top['launches_per_forward']} per forward",
+                'kernel_ms': top['ms_per_launch'], 'kernel_share_of_backbone': top['share_of_backbone'],
+                'classes': [describe(k, v) for k, v in by_time if sum(o_['ms'] for o_ in v) / total >= 0.03],
                 'all_conv': {'tflops': gemm_flops / (gemm_ms * 1e-3) / 1e12, 'ms': gemm_ms, 'share_of_backbone': gemm_ms / total},
                 'backbone_ms_profiled': total,
                 'whole_step': {'tflops': step_flops / (ms_res / args.steps * 1e-3) / 1e12, 'peak': peak_sus * world,

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VP_ABI_VERSION 3
+#define VP_ABI_VERSION 4
 
 enum {
   VP_OK = 0,
@@ -173,7 +173,7 @@ typedef struct vp_op {
   int32_t act, act2;       /* y = act2(act(acc + bias + ubias) * post_s + post_h) * gate + res)  -- see DESIGN.md */
   int32_t seg_len, n_seg;  /* gate / ubias / SEG_CONTEXT rows per utterance: row (b*n_seg + min(t/seg_len, n_seg-1)) */
   float   eps;
-  int32_t tc_bn;           /* N tile of w_tc: 256 if Cout >= 256 else Cout rounded up to 16 */
+  int32_t tc_bn;           /* N tile of w_tc: 256 if Cout >= 256 and tc_kc == 0, else 128 if Cout >= 128, else Cout rounded up to 16 */
   int32_t sum_ld, sum_coff;
   /* fp16 two-term image of w for the kind::f16 variant of the tcgen05 engine (VP_ENGINE_TC16; VPB_TC_F16=0 disables it
    * at run time).  w_tc16_q = (byte offset in the weight arena >> 4) + 1, 0 = none; layout
@@ -188,6 +188,12 @@ typedef struct vp_op {
    * below 2^14, so the split is range-safe whatever the magnitude of the activations.  0 = none: the op then never runs
    * on the fp16 split (it stays on split-TF32, which has fp32's range). */
   int32_t amax_out, amax_in;
+  /* Accumulation chunk of the tcgen05 engines: 0 = the whole K extent goes into one TMEM accumulator; > 0 (a multiple of
+   * 64) = every tc_kc K elements go into a fresh accumulator and the epilogue warps fold the chunks with correctly
+   * rounded fp32 adds.  The tensor core truncates on every accumulate (a bias that grows linearly with the chain
+   * length); deep networks set a short chunk on their long-K layers.  A chunked op uses tc_bn <= 128 (third TMEM region). */
+  int32_t tc_kc;
+  int32_t reserved0;
 } vp_op;
 
 /* Upload the packed fp32 weight arena (host pointer, copied to the device; replaces any previous arena). */

@@ -555,7 +555,7 @@ static void fill_conv(const vp_program* p, const vp_op& o, const float* feats, f
   c.dst = const_cast<float*>(rd(p, o.dst, feats, emb));
   c.sum = const_cast<float*>(rd(p, o.sum, feats, emb)); c.sum_ld = o.sum_ld; c.sum_coff = o.sum_coff;
   c.res = rd(p, o.res, feats, emb); c.gate = rd(p, o.gate, feats, emb); c.ubias = rd(p, o.ubias, feats, emb);
-  c.w = wt(p, o.w); c.w_tc = wt(p, o.w_tc); c.tc_bn = o.tc_bn; c.bias = wt(p, o.bias); c.pre_s = wt(p, o.pre_s); c.pre_h = wt(p, o.pre_h);
+  c.w = wt(p, o.w); c.w_tc = wt(p, o.w_tc); c.tc_bn = o.tc_bn; c.tc_kc = o.tc_kc; c.bias = wt(p, o.bias); c.pre_s = wt(p, o.pre_s); c.pre_h = wt(p, o.pre_h);
   c.post_s = wt(p, o.post_s); c.post_h = wt(p, o.post_h);
   c.B = o.B; c.Tin = o.Tin; c.Fin = o.Fin; c.Cin = o.Cin;
   c.CinTot = o.Cin + (o.src2_mode == VP_SRC2_CONCAT ? o.Cin2 : 0);

@@ -69,7 +69,7 @@ struct ConvParams {
   int src2_mode, src2_ld, src2_coff;
   int Tout, Fout, out_ld, out_coff, res_ld, res_coff;
   int KT, KF, sT, sF, dT, dF, padT, padF, pad_mode;
-  int w_ld, pre_relu, act, act2, seg_len, n_seg, tc_bn, sum_ld, sum_coff;
+  int w_ld, pre_relu, act, act2, seg_len, n_seg, tc_bn, tc_kc, sum_ld, sum_coff;
   unsigned* amax_out;                // slot this op maxes |y| into (or null)
   const unsigned* amax_in;           // slot holding max |x| of the source tensor (fp16 split only, else null)
 };
@@ -106,6 +106,21 @@ __device__ __forceinline__ void amax_commit(unsigned* slot, float m) {     // wh
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
 }
+// Same for kernels with thousands of CTAs: reduce over the whole block first -- one atomic per CTA, not per warp (38 k
+// atomics on one address cost the ew kernel 13 us in round 2).  Every thread of the block must call; blockDim <= 1024.
+__device__ __forceinline__ void amax_commit_block(unsigned* slot, float m) {
+  __shared__ float amax_red[32];
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) amax_red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = (blockDim.x + 31) >> 5;
+    float v = threadIdx.x < nw ? amax_red[threadIdx.x] : 0.f;
+    v = warp_max(v);
+    if (threadIdx.x == 0 && v > 0.f) atomicMax(slot, __float_as_uint(v));
+  }
+}
+
 // exponent s such that amax * 2^s lies in [2^13, 2^14): fp16 hi terms stay below 65504, lo terms above the subnormals
 __device__ __forceinline__ int f16_scale_exp(unsigned amax_bits) {
   const int be = (int)((amax_bits >> 23) & 0xffu);

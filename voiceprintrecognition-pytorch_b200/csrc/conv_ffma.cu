@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256, 2) conv_ffma_kernel(const __grid_constant
         }
     }
   }
-  if (p.amax_out) amax_commit(p.amax_out, tmax);
+  if (p.amax_out) amax_commit_block(p.amax_out, tmax);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) linear_small_m_kernel(const __grid_consta
     sum_add1(p, m, n, y);
     tmax = fabsf(y);
   }
-  if (p.amax_out) amax_commit(p.amax_out, tmax);
+  if (p.amax_out) amax_commit_block(p.amax_out, tmax);
 }
 
 static bool small_m_ok(const ConvParams& p) {
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) conv_c1_kernel(const __grid_constant__ Co
     *reinterpret_cast<float4*>(p.dst + (size_t)m * p.out_ld + p.out_coff + n) = o;
     tmax = amax4(tmax, o);
   }
-  if (p.amax_out) amax_commit(p.amax_out, tmax);
+  if (p.amax_out) amax_commit_block(p.amax_out, tmax);
 }
 
 // Wide variant for the usual stems (N = 16 / 32 / 64 output channels, plain bias -> act -> affine -> act2 epilogue): one
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(256) conv_c1_wide_kernel(const __grid_constant
       }
     }
   }
-  if (p.amax_out) amax_commit(p.amax_out, tmax);
+  if (p.amax_out) amax_commit_block(p.amax_out, tmax);
 }
 
 cudaError_t launch_conv_c1(const ConvParams& p, cudaStream_t stream) {

@@ -32,12 +32,21 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 32;                  // fp32 elements per stage row = 128 B = one SWIZZLE_128B row
 constexpr int A_TILE = BM * BK * 4;     // 16 KB per (hi|lo) A tile
+#ifndef VPB_EPI_WARPS
+#define VPB_EPI_WARPS 4
+#endif
+// Epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, each taking every other 32-column chunk).  With
+// 128 x 256 tiles four warps were the pacing role (ncu, round 2: the MMA warp waited on tmem_empty); the layers whose
+// tiles are short in K are pure output streaming and need the store parallelism.
+constexpr int EPI_WARPS = VPB_EPI_WARPS;
+static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "epilogue warps: one or two per TMEM lane quadrant");
+constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int PRODUCER_WARPS = 8;
 constexpr int PRODUCER_THREADS = PRODUCER_WARPS * 32;      // 256
-constexpr int NUM_THREADS = 128 + PRODUCER_THREADS + 64;   // 4 epilogue + 8 producer + loader + MMA warps
+constexpr int NUM_THREADS = EPI_THREADS + PRODUCER_THREADS + 64;   // epilogue + 8 producer + loader + MMA warps
 constexpr int ROWS_PER_THREAD = BM * 8 / PRODUCER_THREADS;   // 4
-constexpr int SMEM_BUDGET = 200 * 1024;            // pipeline stages
-constexpr int EPI_PAD_BYTES = 4 * 32 * 36 * 4;       // 4 epilogue warps x (32 rows x 36 floats) transpose pads
+constexpr int SMEM_BUDGET = 193 * 1024;            // pipeline stages (+ 32 KB epilogue pads + 1 KB alignment <= 227 KB)
+constexpr int EPI_PAD_BYTES = EPI_WARPS * 32 * 32 * 4;      // per epilogue warp: a 32 x 32-float transpose pad (XOR-swizzled chunks)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -205,7 +214,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull0 + 8 * i, 1);
-      mbar_init(tempty0 + 8 * i, 128);                         // 128 epilogue threads
+      mbar_init(tempty0 + 8 * i, EPI_THREADS);                 // every epilogue thread arrives once per accumulator
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -229,11 +238,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   const int m_groups = (a.m_tiles + C - 1) / C;
   const int total_groups = m_groups * a.n_tiles;
 
-  if (warp >= 4 && warp < 4 + PRODUCER_WARPS) {
+  if (warp >= EPI_WARPS && warp < EPI_WARPS + PRODUCER_WARPS) {
     // =========================== A producers ===========================
     // Thread t owns the 16-byte chunk `chunk` of rows r0 + 32*i: a warp-level load covers 4 rows x 128 contiguous bytes.
     // All tap / channel arithmetic is per K block (uniform over the thread's rows); per row only the bounds test remains.
-    const int t = threadIdx.x - 128;
+    const int t = threadIdx.x - EPI_THREADS;
     const int chunk = t & 7;
     const int r0 = t >> 3;                 // 0..31
     const bool pointwise = (p.KT * p.KF == 1);
@@ -391,7 +400,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
       }
     }
-  } else if (warp == 4 + PRODUCER_WARPS) {
+  } else if (warp == EPI_WARPS + PRODUCER_WARPS) {
     // =========================== B loader (bulk async copy) ===========================
     if (lane == 0) {
       int s = 0;
@@ -414,7 +423,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
       }
     }
-  } else if (warp == 5 + PRODUCER_WARPS) {
+  } else if (warp == EPI_WARPS + 1 + PRODUCER_WARPS) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       // kind::tf32 instruction descriptor: D=F32 (bit 4), A=B=TF32 (2 at bits 7 and 10), K-major, N>>3 @17, M>>4 @24
@@ -466,11 +475,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
   } else {
     // =========================== epilogue (warps 0-3 <-> TMEM lanes 32*warp ..) ===========================
     // Per 32-column chunk: tcgen05.ld gives each thread (= accumulator row) 32 consecutive columns; the chunk is
-    // transposed through a private 32 x 36-float shared-memory pad so that the fused epilogue and the global stores run
+    // transposed through a private 32 x 32-float swizzled shared-memory pad so that the fused epilogue and the global stores run
     // with lanes along N: every store/residual instruction covers 4 rows x 128 contiguous bytes, and the per-column
     // parameters are one float4 per chunk.
-    float* pad = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)S * stage_bytes) + warp * (32 * 36);
-    const uint32_t pad_u32 = smem_base + S * stage_bytes + warp * (32 * 36 * 4);
+    // pad: [32 rows][8 chunks of 4 floats], chunk position XOR-swizzled by (row & 7): row-per-thread float4 writes and
+    // column-per-lane float4 reads are both bank-conflict free at 128 bytes per row (no padding column)
+    float* pad = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)S * stage_bytes) + warp * (32 * 32);
+    const uint32_t pad_u32 = smem_base + S * stage_bytes + warp * (32 * 32 * 4);
+    const int quad = warp & 3;               // TMEM lane quadrant (rows 32 * quad .. of the tile)
+    const int chalf = warp >> 2;             // with 8 epilogue warps: this warp takes the chunks c0 / 32 == chalf (mod 2)
+    constexpr int CSTEP = 32 * (EPI_WARPS / 4);
     const int cg = (lane & 7) * 4;           // this thread's 4 columns inside the chunk
     const int rsub = lane >> 3;              // rows rsub + 4*i
     const bool need_urow = (p.gate != nullptr) || (p.ubias != nullptr);
@@ -478,7 +492,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     // were ~100 instructions per element x 32 elements x 2 call sites = more than half of the kernel's 11 k SASS
     // instructions, and ncu showed `stall_no_instruction` (instruction-cache misses) at 1.4 per issued instruction.
     uint32_t ccount = 0;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t run_col = (uint32_t)(2 * BN);   // running-sum accumulator (only when n_chunks > 1)
     float descale = 1.f;                           // fp16 split: 2^-k of the weight image x 2^-s of the activation scale
     if constexpr (F16) descale = a.descale * exp2i(-f16_scale_exp(__ldg(p.amax_in)));
@@ -493,16 +507,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     const size_t row4 = (size_t)4 * p.out_ld;      // floats between the rows rsub + 4i and rsub + 4(i+1)
     const size_t res4 = (size_t)4 * p.res_ld;
     for (int g = cluster_id; g < total_groups; g += n_clusters) {
-      const int mbase = ((g / a.n_tiles) * (int)C + (int)crank) * BM + warp * 32;
+      const int mbase = ((g / a.n_tiles) * (int)C + (int)crank) * BM + quad * 32;
       const int n0 = (g % a.n_tiles) * BN;
-      if (simple && mbase + 32 <= p.M && n0 + BN <= p.N) {
+      if (simple && mbase + 32 <= p.M && n0 + BN <= p.N && (BN & 31) == 0) {
         float* o0 = p.dst + (size_t)(mbase + rsub) * p.out_ld + p.out_coff + n0 + cg;
         const float* r0 = p.res ? p.res + (size_t)(mbase + rsub) * p.res_ld + p.res_coff + n0 + cg : nullptr;
         for (int ch = 0; ch + 1 < a.n_chunks; ++ch, ++ccount) {      // chunk folding exactly as in the general path
           const int accf = ccount & 1;
           mbar_wait(tfull0 + 8 * accf, (ccount >> 1) & 1);
           tc_fence_after();
-          for (int c0 = 0; c0 < BN; c0 += 32) {
+          for (int c0 = 32 * chalf; c0 < BN; c0 += CSTEP) {
             float v[32];
             tmem_ld32(tmem_base + lane_base + (uint32_t)(accf * BN + c0), v);
             if (ch > 0) {
@@ -520,7 +534,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         mbar_wait(tfull0 + 8 * acc, (ccount >> 1) & 1);
         ++ccount;
         tc_fence_after();
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 32 * chalf; c0 < BN; c0 += CSTEP) {
           const int n = n0 + c0 + cg;
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = b4;
           if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
@@ -537,13 +551,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] += r[j];
             }
-            if (c0 + 32 >= BN) {
+            if (c0 + CSTEP >= BN) {
               tc_fence_before();
               mbar_arrive(tempty0 + 8 * acc);
             }
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pad_u32 + (uint32_t)(lane * 36 + j) * 4u), "f"(v[j]),
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pad_u32 + (uint32_t)(lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) * 4u), "f"(v[j]),
                            "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
                            : "memory");
           }
@@ -556,7 +570,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float4 x = *reinterpret_cast<const float4*>(pad + (rsub + 4 * i) * 36 + cg);
+            float4 x = *reinterpret_cast<const float4*>(pad + (rsub + 4 * i) * 32 + ((((lane & 7) ^ ((rsub + 4 * i) & 7))) << 2));
             x.x = fmaf(x.x, descale, b4.x); x.y = fmaf(x.y, descale, b4.y);      // descale == 1 on the tf32 path
             x.z = fmaf(x.z, descale, b4.z); x.w = fmaf(x.w, descale, b4.w);
             if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
@@ -570,6 +584,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           }
           __syncwarp();
         }
+        if (32 * chalf >= BN) {                     // this warp has no chunk on tiles this narrow: still release the buffer
+          tc_fence_before();
+          mbar_arrive(tempty0 + 8 * acc);
+        }
         continue;
       }
       // per-tile row validity (rows rsub + 4i of this warp's 32)
@@ -581,7 +599,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         const int accf = ccount & 1;
         mbar_wait(tfull0 + 8 * accf, (ccount >> 1) & 1);
         tc_fence_after();
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 32 * chalf; c0 < BN; c0 += CSTEP) {
           float v[32];
           tmem_ld32(tmem_base + lane_base + (uint32_t)(accf * BN + c0), v);
           if (ch > 0) {
@@ -599,7 +617,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
       mbar_wait(tfull0 + 8 * acc, (ccount >> 1) & 1);
       ++ccount;
       tc_fence_after();
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 32 * chalf; c0 < BN; c0 += CSTEP) {
         const int n = n0 + c0 + cg;
         const bool nok = n < p.N;
         // per-column parameters first: their latency hides behind the TMEM load + transpose
@@ -620,13 +638,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += r[j];
           }
-          if (c0 + 32 >= BN) {                // last read of this accumulator buffer: hand it back to the MMA warp
+          if (c0 + CSTEP >= BN) {             // last read of this accumulator buffer: hand it back to the MMA warp
             tc_fence_before();
             mbar_arrive(tempty0 + 8 * acc);
           }
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pad_u32 + (uint32_t)(lane * 36 + j) * 4u), "f"(v[j]),
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(pad_u32 + (uint32_t)(lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) * 4u), "f"(v[j]),
                          "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
                          : "memory");
         }
@@ -639,7 +657,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
           for (int i = 0; i < 8; ++i) {
             if (!(rowok & (1u << i))) continue;
             const int m = mbase + rsub + 4 * i;
-            float4 x = *reinterpret_cast<const float4*>(pad + (rsub + 4 * i) * 36 + cg);
+            float4 x = *reinterpret_cast<const float4*>(pad + (rsub + 4 * i) * 32 + ((((lane & 7) ^ ((rsub + 4 * i) & 7))) << 2));
             // acc * descale + bias in one rounding (descale == 1 on the tf32 path: exactly acc + bias) -- the same
             // expression as the fast path, so a row's result does not depend on which path its tile took
             x.x = fmaf(x.x, descale, b4.x); x.y = fmaf(x.y, descale, b4.y);
@@ -676,6 +694,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
         }
         __syncwarp();
       }
+      if (32 * chalf >= BN) {                       // no chunk for this warp on tiles this narrow: still release the buffer
+        tc_fence_before();
+        mbar_arrive(tempty0 + 8 * acc);
+      }
     }
     if (p.amax_out) amax_commit(p.amax_out, tmax);     // one atomicMax per epilogue warp per launch
   }
@@ -691,16 +713,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
 
 }  // namespace tc
 
-// Host-visible tiling rule (mirrored by the Python packer mvector/engine.py::tc_tile_n).
-// Layers with K > 1536 are accumulated in chunks (see the MMA issuer) and need a third TMEM accumulator -> N tile <= 128.
-// VPB_TC_CHUNK_K / VPB_TC_KC (dev knobs, must be set identically for the Python packer): layers with K above the first are
-// accumulated in chunks of the second (a multiple of 64)
-static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
-static int chunk_threshold() { static int v = env_int("VPB_TC_CHUNK_K", 1536); return v; }
-static int chunk_elems() { static int v = env_int("VPB_TC_KC", 512); return (v >= 64 && v % 64 == 0) ? v : 512; }
-static bool tc_chunked(int K) { return K > chunk_threshold(); }
-static int tc_tile_n(int N, int K) {
-  if (N >= 256 && !tc_chunked(K)) return 256;
+// Host-visible tiling rule (mirrored by the Python packer mvector/engine.py::tc_tile_n).  Chunked layers (vp_op.tc_kc > 0,
+// see the MMA issuer) need a third TMEM accumulator for the running sum -> N tile <= 128.
+static int tc_tile_n(int N, bool chunked) {
+  if (N >= 256 && !chunked) return 256;
   if (N >= 128) return 128;
   return (N + 15) & ~15;
 }
@@ -709,7 +725,8 @@ bool conv_tc_supported(const ConvParams& p) {
   if (p.w_tc == nullptr) return false;
   if (p.M < 1024) return false;                       // tiny-M ops (SE / ASP bias / final FC) stay on the exact FFMA engine
   if (p.N < 16 || (p.N & 3) || (p.K & 3)) return false;
-  if (p.tc_bn != tc_tile_n(p.N, p.K)) return false;
+  if (p.tc_kc < 0 || (p.tc_kc & 63)) return false;
+  if (p.tc_bn != tc_tile_n(p.N, p.tc_kc > 0)) return false;
   // the BN-ReLU prologue gather (MODE 2) reads one source only: prologue + second source stays on the FFMA engine, whose
   // gather composes both (common.cuh::gather_a4)
   if (p.pre_s != nullptr && p.src2_mode != VP_SRC2_NONE) return false;
@@ -754,7 +771,7 @@ static cudaError_t launch_conv_tc_impl(const ConvParams& p, const float* w_img, 
   a.m_tiles = (p.M + BM - 1) / BM;
   a.n_tiles = (p.N + a.BN - 1) / a.BN;
   a.k_blocks = (p.K + bke - 1) / bke;
-  a.kc = tc_chunked(p.K) ? chunk_elems() / bke : a.k_blocks;       // chunks of 512 K elements either way
+  a.kc = (p.tc_kc > 0 && p.tc_kc < p.K) ? p.tc_kc / bke : a.k_blocks;
   a.n_chunks = (a.k_blocks + a.kc - 1) / a.kc;
   // accumulator regions [acc*BN, +BN) (+ running sum at 2*BN when chunked); tcgen05.ld reads 32 columns at a time, so
   // the last 32-column read of the last region must stay inside the allocation

@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(256) ew_kernel(const __grid_constant__ EwParam
     *reinterpret_cast<float4*>(p.dst + m * p.out_ld + p.out_coff + c) = v;
     tmax = amax4(tmax, v);
   }
-  if (p.amax_out) amax_commit(p.amax_out, tmax);
+  if (p.amax_out) amax_commit_block(p.amax_out, tmax);
 }
 
 // dst[r, 0:C_out] = (x[r, 0:C], 0 ...): scalar, for feature dims that are not multiples of 4 (Spectrogram's n_fft/2+1 bins)
@@ -319,19 +319,19 @@ __global__ void __launch_bounds__(256) pad_copy_kernel(const __grid_constant__ E
     p.dst[m * p.out_ld + p.out_coff + c] = v;
     tmax = fmaxf(tmax, fabsf(v));
   }
-  if (p.amax_out) amax_commit(p.amax_out, tmax);
+  if (p.amax_out) amax_commit_block(p.amax_out, tmax);
 }
 
 cudaError_t launch_ew(const EwParams& p, cudaStream_t stream) {
   if (p.mode == VP_EW_PAD_COPY) {
     long long blocks = (p.rows * p.C_out + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks > 148 * 16) blocks = 148 * 16;
     launch_pdl(pad_copy_kernel, (int)(blocks < 1 ? 1 : blocks), 256, 0, stream, p);
     return cudaGetLastError();
   }
   long long total = p.rows * (p.C >> 2);
   long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
   launch_pdl(ew_kernel, (int)blocks, 256, 0, stream, p);
   return cudaGetLastError();
@@ -372,13 +372,13 @@ __global__ void __launch_bounds__(256) pool2d_kernel(const __grid_constant__ Poo
     *reinterpret_cast<float4*>(p.dst + ((size_t)(b * p.Tout + to) * p.Fout + fo) * p.out_ld + p.out_coff + c) = acc;
     tmax = amax4(tmax, acc);
   }
-  if (p.amax_out) amax_commit(p.amax_out, tmax);
+  if (p.amax_out) amax_commit_block(p.amax_out, tmax);
 }
 
 cudaError_t launch_pool2d(const PoolParams& p, cudaStream_t stream) {
   long long total = (long long)p.B * p.Tout * p.Fout * (p.C >> 2);
   long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
   launch_pdl(pool2d_kernel, (int)blocks, 256, 0, stream, p);
   return cudaGetLastError();

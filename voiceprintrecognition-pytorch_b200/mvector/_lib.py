@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libvpb200.so')
+LIB_PATH = os.environ.get('VPB_LIB') or os.path.join(os.path.dirname(_HERE), 'libvpb200.so')   # VPB_LIB: dev builds (A/B runs)
 
 VP_OK, VP_ERR_INVALID, VP_ERR_CUDA, VP_ERR_NOMEM, VP_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 OP_CONV, OP_CONV_C1, OP_COLSTATS, OP_ASP_POOL, OP_EW, OP_POOL2D = 1, 2, 3, 4, 5, 6
@@ -37,7 +37,7 @@ class Op(C.Structure):
                                             'KT', 'KF', 'sT', 'sF', 'dT', 'dF', 'padT', 'padF', 'pad_mode',
                                             'w_ld', 'pre_relu', 'act', 'act2', 'seg_len', 'n_seg')]
                 + [('eps', C.c_float), ('tc_bn', C.c_int32), ('sum_ld', C.c_int32), ('sum_coff', C.c_int32),
-                   ('w_tc16_q', C.c_int32), ('tc16_descale', C.c_float), ('amax_out', C.c_int32), ('amax_in', C.c_int32)])
+                   ('w_tc16_q', C.c_int32), ('tc16_descale', C.c_float), ('amax_out', C.c_int32), ('amax_in', C.c_int32), ('tc_kc', C.c_int32), ('reserved0', C.c_int32)])
 
 
 class VpError(RuntimeError):
@@ -95,7 +95,7 @@ def lib():
         fn = getattr(L, name)          # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if L.vp_abi_version() != 3:
+    if L.vp_abi_version() != 4:
         raise RuntimeError('libvpb200.so ABI version mismatch')
     if L.vp_sizeof_op() != C.sizeof(Op) or L.vp_sizeof_frontend_desc() != C.sizeof(FrontendDesc):
         raise RuntimeError('vp_op / vp_frontend_desc layout mismatch between the ctypes binding and libvpb200.so')

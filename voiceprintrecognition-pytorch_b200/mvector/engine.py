@@ -78,10 +78,13 @@ class Engine:
 class WeightArena:
     """Packs fp32 tensors into one blob; returns byte offsets (256 B aligned)."""
 
-    def __init__(self):
+    def __init__(self, chunk_k=1536, kc=512):
         self._chunks = []
         self._size = 0
         self.index = OrderedDict()
+        # accumulation-chunk policy of the tcgen05 engines (vp_op.tc_kc): layers with K > chunk_k are accumulated in
+        # chunks of kc K elements (bounded tensor-core accumulate truncation); deep nets choose shorter values
+        self.chunk_k, self.kc = chunk_k, kc
 
     def add(self, name, arr):
         a = np.ascontiguousarray(np.asarray(arr, dtype=np.float32)).reshape(-1)
@@ -100,9 +103,10 @@ class WeightArena:
         W2d = np.asarray(W2d, dtype=np.float64)
         d = {'w': self.add(name, W2d)}
         if tc and W2d.shape[0] >= 16 and W2d.shape[0] % 4 == 0 and W2d.shape[1] % 4 == 0:
-            img, bn = pack_tc(W2d)
+            kc = self.kc if W2d.shape[1] > self.chunk_k else 0
+            img, bn = pack_tc(W2d, chunked=kc > 0)
             d['w_tc'] = self.add(name + '.tc', img)
-            d['tc_bn'] = bn
+            d['tc_bn'], d['tc_kc'] = bn, kc
             if TC_F16 and W2d.shape[0] >= 128 and W2d.shape[1] >= 8 and W2d.shape[1] % 8 == 0:      # fp16 two-term image (VP_ENGINE_TC16)
                 img16, descale = pack_tc16(W2d, bn)
                 d['w_tc16'] = self.add(name + '.tc16', img16)
@@ -113,10 +117,10 @@ class WeightArena:
         return np.concatenate(self._chunks) if self._chunks else np.zeros(64, dtype=np.float32)
 
 
-def tc_tile_n(N, K=0):
-    """N tile of the tcgen05 engine (must match conv_tc.cu::tc_tile_n): 256-wide tiles, except for long-K layers
-    (K > 1536) whose chunked accumulation keeps a third TMEM accumulator and therefore uses 128-wide tiles."""
-    if N >= 256 and K <= int(os.environ.get('VPB_TC_CHUNK_K', '1536')):
+def tc_tile_n(N, chunked=False):
+    """N tile of the tcgen05 engine (must match conv_tc.cu::tc_tile_n): 256-wide tiles, except for layers with chunked
+    accumulation (vp_op.tc_kc > 0), which keep a third TMEM accumulator and therefore use 128-wide tiles."""
+    if N >= 256 and not chunked:
         return 256
     if N >= 128:
         return 128
@@ -129,11 +133,12 @@ def tf32_rna(x):
     return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
 
 
-def pack_tc(W):
+def pack_tc(W, chunked=None):
     """[N, K] -> (float32 image [n_tiles, k_blocks, 2(hi|lo), BN, 32] with SWIZZLE_128B chunk permutation, BN).
-    hi = tf32(W), lo = W - hi (exact in fp32).  Rows >= N / columns >= K are zero."""
+    hi = tf32(W), lo = W - hi (exact in fp32).  Rows >= N / columns >= K are zero.  ``chunked`` (default: K > 1536)
+    selects the 128-wide tiles of layers with chunked accumulation."""
     N, K = W.shape
-    bn = tc_tile_n(N, K)
+    bn = tc_tile_n(N, K > 1536 if chunked is None else chunked)
     nt, kb = (N + bn - 1) // bn, (K + 31) // 32
     Wp = np.zeros((nt * bn, kb * 32), dtype=np.float32)
     Wp[:N, :K] = W.astype(np.float32)
@@ -304,7 +309,7 @@ class PlanBuilder:
         o.Tin, o.Fin, o.Tout, o.Fout = Tin, Fin, Tout, Fout
         o.KT, o.KF, o.sT, o.sF, o.dT, o.dF, o.padT, o.padF, o.pad_mode = KT, KF, sT, sF, dT, dF, padT, padF, pad_mode
         if isinstance(w, dict):            # packed by WeightArena.add_conv: plain + optional tensor-core image
-            o.w, o.w_tc, o.tc_bn = w['w'], w.get('w_tc', -1), w.get('tc_bn', 0)
+            o.w, o.w_tc, o.tc_bn, o.tc_kc = w['w'], w.get('w_tc', -1), w.get('tc_bn', 0), w.get('tc_kc', 0)
             if 'w_tc16' in w:
                 o.w_tc16_q, o.tc16_descale = (w['w_tc16'] >> 4) + 1, w['tc16_descale']
         else:

@@ -26,6 +26,11 @@ class Backbone:
     """Base of the model mirrors.  A backbone is *lowered* for a concrete (B, T) into a vp_program; programs are
     cached per shape.  Calling the object runs features [B, T, F] (CUDA fp32) -> embeddings [B, embd_dim]."""
 
+    #: (chunk_k, kc): layers with K > chunk_k accumulate in chunks of kc K elements on the tensor cores (vp_op.tc_kc).  The
+    #: tensor core truncates on every accumulate, a bias that adds up coherently through a deep network: the shallow TDNNs
+    #: keep single-accumulator GEMMs up to K = 1536, the deep 2-D residual nets override this with shorter chains.
+    tc_chunk_policy = (1536, 512)
+
     #: parameter-name -> shape, filled by subclasses (reference state_dict layout, without the ``0.`` prefix)
     def param_shapes(self):
         raise NotImplementedError
@@ -77,7 +82,7 @@ class Backbone:
             raise RuntimeError('missing weights for: ' + ', '.join(missing[:8]) + (' ...' if len(missing) > 8 else ''))
         if engine is not None:
             self.engine = engine
-        arena = WeightArena()
+        arena = WeightArena(*self.tc_chunk_policy)
         self._off = {}
         self._pack(sd, arena)
         self._blob = arena.blob()          # uploaded lazily: ingesting weights / lowering needs no GPU
