@@ -307,8 +307,8 @@ def run_gpu_arm(args, cfg):
     from mvector import _lib as L
     from mvector import distributed as mdist
     from mvector.predict import MVectorPredictor
-    if world > 1:
-        mdist.bind_rank_to_local_cpus(local, int(os.environ.get('LOCAL_WORLD_SIZE', world)))
+    bound = mdist.bind_rank_to_local_cpus(local, int(os.environ.get('LOCAL_WORLD_SIZE', world)))
+    mark(f'cpu affinity: {len(bound) if bound else "unchanged"}')
 
     td_obj = tempfile.TemporaryDirectory()
     td = td_obj.name

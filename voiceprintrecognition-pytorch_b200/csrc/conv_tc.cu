@@ -758,16 +758,11 @@ static cudaError_t launch_conv_tc_impl(const ConvParams& p, const float* w_img, 
   a.BN = p.tc_bn;
   const int bke = f16 ? 64 : BK;
   const int stage_bytes = 2 * A_TILE + 2 * a.BN * 128;
-  // Multi-tap convs on narrow tiles re-read every input element KT*KF times and are gather-, not tensor-bound: a smaller
-  // pipeline leaves the rest of the 228 KB to the L1, which then serves the repeated taps instead of the L2
-  // (VPB_TC_NARROW_KB: shared-memory budget in KB for those layers; measured in profiles/r2_narrow_l1.md).
-  static int narrow_kb = -1;
-  if (narrow_kb < 0) { const char* ev = getenv("VPB_TC_NARROW_KB"); narrow_kb = ev ? atoi(ev) : 200; if (narrow_kb < 64 || narrow_kb > 200) narrow_kb = 200; }
-  const int budget = (p.KT * p.KF > 1 && a.BN <= 64) ? narrow_kb * 1024 : SMEM_BUDGET;
-  a.stages = budget / stage_bytes;
+  // (Round 2 tried a smaller pipeline for narrow multi-tap layers so that the L1 would serve the repeated taps: no effect,
+  // removed -- profiles/r2_ncu_conv_tc.md section 4.)
+  a.stages = SMEM_BUDGET / stage_bytes;
   if (a.stages > 8) a.stages = 8;
-  if (a.stages < 2) a.stages = 2;
-  if (a.stages * stage_bytes > SMEM_BUDGET) return cudaErrorInvalidConfiguration;
+  if (a.stages < 2) return cudaErrorInvalidConfiguration;
   a.m_tiles = (p.M + BM - 1) / BM;
   a.n_tiles = (p.N + a.BN - 1) / a.BN;
   a.k_blocks = (p.K + bke - 1) / bke;

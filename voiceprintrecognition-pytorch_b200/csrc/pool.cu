@@ -325,13 +325,13 @@ __global__ void __launch_bounds__(256) pad_copy_kernel(const __grid_constant__ E
 cudaError_t launch_ew(const EwParams& p, cudaStream_t stream) {
   if (p.mode == VP_EW_PAD_COPY) {
     long long blocks = (p.rows * p.C_out + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > 148 * 32) blocks = 148 * 32;
     launch_pdl(pad_copy_kernel, (int)(blocks < 1 ? 1 : blocks), 256, 0, stream, p);
     return cudaGetLastError();
   }
   long long total = p.rows * (p.C >> 2);
   long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > 148 * 32) blocks = 148 * 32;
   if (blocks < 1) blocks = 1;
   launch_pdl(ew_kernel, (int)blocks, 256, 0, stream, p);
   return cudaGetLastError();
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256) pool2d_kernel(const __grid_constant__ Poo
 cudaError_t launch_pool2d(const PoolParams& p, cudaStream_t stream) {
   long long total = (long long)p.B * p.Tout * p.Fout * (p.C >> 2);
   long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > 148 * 32) blocks = 148 * 32;
   if (blocks < 1) blocks = 1;
   launch_pdl(pool2d_kernel, (int)blocks, 256, 0, stream, p);
   return cudaGetLastError();

@@ -47,7 +47,22 @@ def bind_rank_to_local_cpus(local_rank, local_world):
         avail = sorted(os.sched_getaffinity(0))
     except AttributeError:
         return None
-    if local_world <= 1 or len(avail) < 2 * local_world:
+    if len(avail) < 2 * max(local_world, 1):
+        return None
+    if local_world <= 1:
+        # single process: stay on the NUMA node of the GPU (pinned staging buffers are first-touched there and the
+        # gather threads do not wander to the other socket); nothing to do when the platform does not tell
+        node = _gpu_numa_node(local_rank) if torch.cuda.is_available() else None
+        if node is None:
+            return None
+        try:
+            with open(f'/sys/devices/system/node/node{node}/cpulist') as f:
+                cpus = [c for c in _parse_cpulist(f.read()) if c in set(avail)]
+            if len(cpus) >= 2:
+                os.sched_setaffinity(0, cpus)
+                return cpus
+        except Exception:
+            pass
         return None
     nodes = [_gpu_numa_node(i) for i in range(local_world)] if torch.cuda.is_available() else [None] * local_world
     mine = nodes[local_rank] if local_rank < len(nodes) else None

@@ -182,9 +182,9 @@ class MVectorPredictor:
     #: utterances per backbone program (one fused vp_embed per chunk); the workspace limit can lower it for big 2-D nets
     MAX_BATCH = int(os.environ.get('VPB_PREDICT_CHUNK', '256'))
     #: utterances per staging call (host gather -> pinned -> H2D -> front-end kernels), double buffered
-    STAGE_ROWS = int(os.environ.get('VPB_STAGE_ROWS', '64'))
+    STAGE_ROWS = int(os.environ.get('VPB_STAGE_ROWS', '128'))
     #: utterances per H2D copy inside a staging call (the copy of slice k overlaps the gather of slice k+1)
-    COPY_SLICE = int(os.environ.get('VPB_COPY_SLICE', '16'))
+    COPY_SLICE = int(os.environ.get('VPB_COPY_SLICE', '8'))
     WS_LIMIT_BYTES = int(float(os.environ.get('VPB_WS_LIMIT_GB', '64')) * 2 ** 30)
 
     @staticmethod
