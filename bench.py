@@ -386,12 +386,14 @@ def run_gpu_arm(args, cfg):
     ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
     mark(f'e2e timing done: {ms_e2e:.2f} ms')
 
-    # consistency of the two paths on this rank: resident and host-staged results of the same batch are bit-identical
+    # consistency of the two paths on this rank: resident and host-staged results of the same batch (same kernels, same
+    # data; the host path cuts the backbone into smaller chunks, so the fp16-split activation scales may differ: a few ulp)
     i_chk = 0
     e_res = step_resident(i_chk).clone()
     e_host = torch.from_numpy(step_e2e(i_chk)).to(dev)
     sync_all()
-    assert torch.equal(e_res, e_host), 'resident and host-staged paths disagree'
+    dis = float(((e_res - e_host).norm(dim=1) / e_res.norm(dim=1)).max())
+    assert dis <= 2e-6, f'resident and host-staged paths disagree: rel-L2 {dis}'
 
     T0 = fz.num_frames(lmax0)
     cb = pred._chunk_size(B, T0)

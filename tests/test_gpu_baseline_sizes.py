@@ -76,8 +76,14 @@ def test_baseline_config_full_batch_vs_oracle(name):
         x[i, :w.shape[0]] = w
     xd = torch.from_numpy(x).cuda()
     e_dev = pred.embed_device(xd, lens)
-    assert np.array_equal(e_dev.cpu().numpy(), e_host)                       # same kernels, same data: bit identical
     assert torch.equal(pred.embed_device(xd, lens), e_dev)                   # deterministic (no float atomics on the path)
+    # host-staged vs device-resident: the same kernels on the same data.  With the same backbone chunking they agree bit
+    # for bit; the default host path uses smaller chunks (to overlap staging with compute), and a chunk's fp16-split
+    # activation scale is a property of the tensor the kernel sees, so the default agrees to a few ulp
+    assert rel_l2(e_host, e_dev.cpu().numpy()).max() <= 2e-6
+    pred.HOST_CHUNK = pred.MAX_BATCH
+    assert np.array_equal(pred.predict_batch(waves), e_dev.cpu().numpy())
+    del pred.HOST_CHUNK
     # (3) >= 16 utterances against the CPU oracle on the same padded batch (first / last / longest / shortest / spread)
     idx = sorted(set([0, B - 1, int(np.argmax(lens)), int(np.argmin(lens))] + list(range(3, B, max(B // 14, 1)))))[:18]
     assert len(idx) >= 16

@@ -278,6 +278,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             rows[i] = decode_row(p, m0 + r0 + 32 * i);
             if (!rows[i].valid) rows[i].t0 = -(1 << 28);        // fails every bounds test below (also after reflection)
           }
+          if (a.debug & 8) {
+            // (VPB_TC_DEBUG bit 3, experiment) pull the centre rows of this CTA's NEXT tile into the L2 while this tile is
+            // being gathered: fire-and-forget, turns the DRAM latency of the narrow, gather-latency-bound layers into L2
+            // hits.  One thread per 128-byte line: chunk c takes the lines c, c + 8, ... of its rows' channel window.
+            const int gn = g + n_clusters;
+            if (gn < total_groups) {
+              const int mn = ((gn / a.n_tiles) * (int)C + (int)crank) * BM;
+              const int lines = (p.Cin * 4 + 127) >> 7;
+#pragma unroll
+              for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+                const RowInfo rn = decode_row(p, mn + r0 + 32 * i);
+                const int tc = rn.t0 + p.padT, fc = rn.f0 + p.padF;       // centre tap of a "same" conv
+                if (rn.valid && (unsigned)tc < (unsigned)p.Tin && (unsigned)fc < (unsigned)p.Fin) {
+                  const float* rp = p.src + (size_t)(rn.base + tc * p.Fin + fc) * p.in_ld + p.in_coff;
+                  for (int l = chunk; l < lines; l += 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + l * 32));
+                }
+              }
+            }
+          }
         }
         const int ci = g_ci;
         const int dt = g_kt * p.dT, df = g_kf * p.dF;
@@ -509,6 +528,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     for (int g = cluster_id; g < total_groups; g += n_clusters) {
       const int mbase = ((g / a.n_tiles) * (int)C + (int)crank) * BM + quad * 32;
       const int n0 = (g % a.n_tiles) * BN;
+      if (p.res) {
+        // Residual tiles are pure streaming (c5: 128 KB per 128 x 256 tile, read once): with only eight 16-byte loads in
+        // flight per epilogue thread the reads were latency bound at ~5 GB/s per SM (15 ms for the M = 5 M, K = 72 layers
+        // of the 55 M ERes2Net).  prefetch.global.L2 is fire-and-forget: pull the NEXT tile's residual rows into the L2
+        // now (and this tile's, on the first iteration), so that the loads below are L2 hits.
+        auto prefetch_tile = [&](int gg) {
+          const int mb = ((gg / a.n_tiles) * (int)C + (int)crank) * BM + quad * 32 + rsub;
+          const float* base = p.res + p.res_coff + (gg % a.n_tiles) * BN + (lane & 7) * 32;
+          if ((lane & 7) * 32 < BN)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (mb + 4 * i < p.M)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)(mb + 4 * i) * p.res_ld));
+        };
+        if (g == cluster_id) prefetch_tile(g);
+        if (g + n_clusters < total_groups) prefetch_tile(g + n_clusters);
+      }
       if (simple && mbase + 32 <= p.M && n0 + BN <= p.N && (BN & 31) == 0) {
         float* o0 = p.dst + (size_t)(mbase + rsub) * p.out_ld + p.out_coff + n0 + cg;
         const float* r0 = p.res ? p.res + (size_t)(mbase + rsub) * p.res_ld + p.res_coff + n0 + cg : nullptr;
