@@ -278,25 +278,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             rows[i] = decode_row(p, m0 + r0 + 32 * i);
             if (!rows[i].valid) rows[i].t0 = -(1 << 28);        // fails every bounds test below (also after reflection)
           }
-          if (a.debug & 8) {
-            // (VPB_TC_DEBUG bit 3, experiment) pull the centre rows of this CTA's NEXT tile into the L2 while this tile is
-            // being gathered: fire-and-forget, turns the DRAM latency of the narrow, gather-latency-bound layers into L2
-            // hits.  One thread per 128-byte line: chunk c takes the lines c, c + 8, ... of its rows' channel window.
-            const int gn = g + n_clusters;
-            if (gn < total_groups) {
-              const int mn = ((gn / a.n_tiles) * (int)C + (int)crank) * BM;
-              const int lines = (p.Cin * 4 + 127) >> 7;
-#pragma unroll
-              for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-                const RowInfo rn = decode_row(p, mn + r0 + 32 * i);
-                const int tc = rn.t0 + p.padT, fc = rn.f0 + p.padF;       // centre tap of a "same" conv
-                if (rn.valid && (unsigned)tc < (unsigned)p.Tin && (unsigned)fc < (unsigned)p.Fin) {
-                  const float* rp = p.src + (size_t)(rn.base + tc * p.Fin + fc) * p.in_ld + p.in_coff;
-                  for (int l = chunk; l < lines; l += 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + l * 32));
-                }
-              }
-            }
-          }
         }
         const int ci = g_ci;
         const int dt = g_kt * p.dT, df = g_kf * p.dF;
@@ -597,13 +578,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
                            "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
                            : "memory");
           }
+          float4 rr[8];
+          if (r0) {
+            // residual: eight 16-byte loads issued as ONE batch (volatile asm: ptxas otherwise sinks every load next to its
+            // use to save registers, which serialises eight DRAM round trips per chunk -- the N = 256, K = 72 layers of the
+            // 55 M ERes2Net took 15 ms that way), before the pad is read back so that the latency overlaps the transpose
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(rr[i].x), "=f"(rr[i].y), "=f"(rr[i].z), "=f"(rr[i].w)
+                           : "l"(r0 + c0 + i * res4));
+          }
           __syncwarp();
           float* o = o0 + c0;
-          float4 rr[8];
-          if (r0) {                                 // residual: all eight loads in flight before the first use
-#pragma unroll
-            for (int i = 0; i < 8; ++i) rr[i] = __ldg(reinterpret_cast<const float4*>(r0 + c0 + i * res4));
-          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4 x = *reinterpret_cast<const float4*>(pad + (rsub + 4 * i) * 32 + ((((lane & 7) ^ ((rsub + 4 * i) & 7))) << 2));

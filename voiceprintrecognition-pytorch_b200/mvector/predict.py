@@ -184,7 +184,7 @@ class MVectorPredictor:
     #: utterances per staging call (host gather -> pinned -> H2D -> front-end kernels), double buffered
     STAGE_ROWS = int(os.environ.get('VPB_STAGE_ROWS', '64'))
     #: utterances per H2D copy inside a staging call (the copy of slice k overlaps the gather of slice k+1)
-    COPY_SLICE = int(os.environ.get('VPB_COPY_SLICE', '16'))
+    COPY_SLICE = int(os.environ.get('VPB_COPY_SLICE', '8'))
     #: utterances per backbone program on the HOST-staged path: smaller than MAX_BATCH so that the backbone of chunk k runs
     #: while the host gathers and copies chunk k+1 (measured on B200, 256 x 3 s: 7.2 ms with one chunk, 6.4 ms with two)
     HOST_CHUNK = int(os.environ.get('VPB_HOST_CHUNK', '128'))
