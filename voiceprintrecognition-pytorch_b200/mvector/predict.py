@@ -182,12 +182,12 @@ class MVectorPredictor:
     #: utterances per backbone program (one fused vp_embed per chunk); the workspace limit can lower it for big 2-D nets
     MAX_BATCH = int(os.environ.get('VPB_PREDICT_CHUNK', '256'))
     #: utterances per staging call (host gather -> pinned -> H2D -> front-end kernels), double buffered
-    STAGE_ROWS = int(os.environ.get('VPB_STAGE_ROWS', '64'))
+    STAGE_ROWS = int(os.environ.get('VPB_STAGE_ROWS', '128'))
     #: utterances per H2D copy inside a staging call (the copy of slice k overlaps the gather of slice k+1)
     COPY_SLICE = int(os.environ.get('VPB_COPY_SLICE', '8'))
     #: utterances per backbone program on the HOST-staged path: smaller than MAX_BATCH so that the backbone of chunk k runs
     #: while the host gathers and copies chunk k+1 (measured on B200, 256 x 3 s: 7.2 ms with one chunk, 6.4 ms with two)
-    HOST_CHUNK = int(os.environ.get('VPB_HOST_CHUNK', '128'))
+    HOST_CHUNK = int(os.environ.get('VPB_HOST_CHUNK', '256'))
     WS_LIMIT_BYTES = int(float(os.environ.get('VPB_WS_LIMIT_GB', '64')) * 2 ** 30)
 
     @staticmethod
