@@ -501,9 +501,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
     // chunk, were the pacing role -- the MMA warp spent its time waiting for tmem_empty).  The common epilogue shape
     // -- bias, optional ReLU, optional BN affine, nothing per utterance, no residual -- on a tile without row / column
     // tails needs no predicates, one pointer per thread and three FP instructions per element.
-    const bool simple = !p.ubias && !p.gate && !p.sum && (p.act == VP_ACT_NONE || p.act == VP_ACT_RELU) &&
-                        (p.act2 == VP_ACT_NONE || p.act2 == VP_ACT_RELU);
-    const bool relu = p.act == VP_ACT_RELU, relu2 = p.act2 == VP_ACT_RELU;
+    // ReLU and the ERes2Net family's ReLU(20) = Hardtanh(0, 20) (eres2net.py:12-17) are both "clamp to [0, hi]" with
+    // hi = +inf / 20: min(max(x, 0), hi), the same expression and order as apply_act.  (ncu, round 2: with Hardtanh left to
+    // the general path every conv of the 55 M ERes2Net ran the rolled row-at-a-time epilogue -- 13.9 ms for a residual
+    // 1x1 conv whose twin without activation took 1.6 ms.)
+    auto clamps = [](int act) { return act == VP_ACT_RELU || act == VP_ACT_HARDTANH20; };
+    const bool simple = !p.ubias && !p.gate && !p.sum && (p.act == VP_ACT_NONE || clamps(p.act)) &&
+                        (p.act2 == VP_ACT_NONE || clamps(p.act2));
+    const bool relu = clamps(p.act), relu2 = clamps(p.act2);
+    const float hi1 = p.act == VP_ACT_HARDTANH20 ? 20.f : INFINITY, hi2 = p.act2 == VP_ACT_HARDTANH20 ? 20.f : INFINITY;
     const size_t row4 = (size_t)4 * p.out_ld;      // floats between the rows rsub + 4i and rsub + 4(i+1)
     const size_t res4 = (size_t)4 * p.res_ld;
     for (int g = cluster_id; g < total_groups; g += n_clusters) {
@@ -596,12 +602,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const __grid_co
             float4 x = *reinterpret_cast<const float4*>(pad + (rsub + 4 * i) * 32 + ((((lane & 7) ^ ((rsub + 4 * i) & 7))) << 2));
             x.x = fmaf(x.x, descale, b4.x); x.y = fmaf(x.y, descale, b4.y);      // descale == 1 on the tf32 path
             x.z = fmaf(x.z, descale, b4.z); x.w = fmaf(x.w, descale, b4.w);
-            if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            if (relu) {
+              x.x = fminf(fmaxf(x.x, 0.f), hi1); x.y = fminf(fmaxf(x.y, 0.f), hi1);
+              x.z = fminf(fmaxf(x.z, 0.f), hi1); x.w = fminf(fmaxf(x.w, 0.f), hi1);
+            }
             if (p.post_s) {
               x.x = fmaf(x.x, s4.x, h4.x); x.y = fmaf(x.y, s4.y, h4.y); x.z = fmaf(x.z, s4.z, h4.z); x.w = fmaf(x.w, s4.w, h4.w);
             }
             if (r0) { x.x += rr[i].x; x.y += rr[i].y; x.z += rr[i].z; x.w += rr[i].w; }
-            if (relu2) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            if (relu2) {
+              x.x = fminf(fmaxf(x.x, 0.f), hi2); x.y = fminf(fmaxf(x.y, 0.f), hi2);
+              x.z = fminf(fmaxf(x.z, 0.f), hi2); x.w = fminf(fmaxf(x.w, 0.f), hi2);
+            }
             *reinterpret_cast<float4*>(o + i * row4) = x;
             tmax = amax4(tmax, x);
           }

@@ -60,9 +60,9 @@ struct Pool {
   void worker(int id) {
     uint64_t seen = 0;
     for (;;) {
-      // a predict_batch issues its staging calls back to back: spin ~0.3 ms for the next job before going to sleep on the
+      // a predict_batch issues its staging calls back to back: spin ~50 us for the next job before going to sleep on the
       // condition variable (a futex wake-up of an idle core costs 50-100 us, more than gathering a slice)
-      for (int spin = 0; spin < 20000 && gen_hint.load(std::memory_order_acquire) == seen; ++spin) {
+      for (int spin = 0; spin < 3000 && gen_hint.load(std::memory_order_acquire) == seen; ++spin) {
 #if defined(__x86_64__)
         __builtin_ia32_pause();
 #endif

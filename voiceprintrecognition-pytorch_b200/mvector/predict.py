@@ -200,7 +200,7 @@ class MVectorPredictor:
         except AttributeError:
             ncpu = os.cpu_count() or 1
         local_world = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
-        return max(1, min(16, ncpu // local_world - 1))
+        return max(1, min(8, ncpu // local_world - 1))
 
     def _pinned_slot(self, slot, n):
         """Two reusable pinned host staging buffers (double buffering)."""
