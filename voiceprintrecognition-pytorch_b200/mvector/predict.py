@@ -200,6 +200,8 @@ class MVectorPredictor:
         except AttributeError:
             ncpu = os.cpu_count() or 1
         local_world = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
+        if ncpu < (os.cpu_count() or ncpu):
+            local_world = 1          # the launcher already gave this rank its own CPU slice (bind_rank_to_local_cpus)
         return max(1, min(8, ncpu // local_world - 1))
 
     def _pinned_slot(self, slot, n):
