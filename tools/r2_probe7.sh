@@ -13,5 +13,5 @@ run() {  # config n steps port
 run c3 8 30 29711
 run c2 8 50 29712
 run c5 4 8 29713
-run c2 4 50 29714
+
 cat gpurun_out/r2_p7_status.log; for f in gpurun_out/r2_p7_bench_*.json; do head -c 500 $f; echo; done; tail -n 3 gpurun_out/r2_p7_bench_c3_n8.err

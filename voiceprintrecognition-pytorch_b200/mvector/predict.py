@@ -187,7 +187,7 @@ class MVectorPredictor:
     COPY_SLICE = int(os.environ.get('VPB_COPY_SLICE', '8'))
     #: utterances per backbone program on the HOST-staged path: smaller than MAX_BATCH so that the backbone of chunk k runs
     #: while the host gathers and copies chunk k+1 (measured on B200, 256 x 3 s: 7.2 ms with one chunk, 6.4 ms with two)
-    HOST_CHUNK = int(os.environ.get('VPB_HOST_CHUNK', '256'))
+    HOST_CHUNK = int(os.environ.get('VPB_HOST_CHUNK', '128'))
     WS_LIMIT_BYTES = int(float(os.environ.get('VPB_WS_LIMIT_GB', '64')) * 2 ** 30)
 
     @staticmethod
