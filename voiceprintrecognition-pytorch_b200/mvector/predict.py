@@ -62,6 +62,7 @@ class MVectorPredictor:
         self._copy_stream = None
         self._ws_per_utt = {}
         self._trace = None
+        self._trace_dev = None
 
         self.speaker_diarize = SpeakerDiarization()
         # similarity matrix of the spectral clustering (speaker_diarization.py:254-257) on the device
@@ -188,6 +189,9 @@ class MVectorPredictor:
     #: utterances per backbone program on the HOST-staged path: smaller than MAX_BATCH so that the backbone of chunk k runs
     #: while the host gathers and copies chunk k+1 (measured on B200, 256 x 3 s: 7.2 ms with one chunk, 6.4 ms with two)
     HOST_CHUNK = int(os.environ.get('VPB_HOST_CHUNK', '128'))
+    # front-end kernels on the main stream, right before their backbone chunk (1), or on the copy stream behind their data (0,
+    # where they sit between two stages' H2D copies and hold the second one up)
+    FE_ON_MAIN = os.environ.get('VPB_FE_STREAM', 'main') == 'main'
     WS_LIMIT_BYTES = int(float(os.environ.get('VPB_WS_LIMIT_GB', '64')) * 2 ** 30)
 
     @staticmethod
@@ -202,7 +206,29 @@ class MVectorPredictor:
         local_world = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
         if ncpu < (os.cpu_count() or ncpu):
             local_world = 1          # the launcher already gave this rank its own CPU slice (bind_rank_to_local_cpus)
-        return max(1, min(8, ncpu // local_world - 1))
+        per_rank = ncpu // local_world
+        quota = MVectorPredictor._cgroup_cpus()
+        if quota is not None:        # a container CPU quota is shared by ALL ranks of the node, bound or not
+            per_rank = min(per_rank, int(quota // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))))
+        return max(1, min(8, per_rank - 1))
+
+    @staticmethod
+    def _cgroup_cpus():
+        """CPUs' worth of time the container may use (cgroup v2 cpu.max / v1 cfs quota), or None when unlimited."""
+        try:
+            with open('/sys/fs/cgroup/cpu.max') as f:
+                q, p = f.read().split()
+            return None if q == 'max' else float(q) / float(p)
+        except Exception:
+            pass
+        try:
+            with open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us') as f:
+                q = float(f.read())
+            with open('/sys/fs/cgroup/cpu/cpu.cfs_period_us') as f:
+                p = float(f.read())
+            return None if q <= 0 else q / p
+        except Exception:
+            return None
 
     def _pinned_slot(self, slot, n):
         """Two reusable pinned host staging buffers (double buffering)."""
@@ -282,49 +308,74 @@ class MVectorPredictor:
         bounds = np.cumsum(self._host_chunks(B, T)).tolist()       # end row of every backbone chunk
         whole = desc.post == 1 and desc.top_db >= 0      # MFCC: the top_db clamp needs the maximum over the whole call
         S = B if whole else min(self.STAGE_ROWS, B)
-        dwave = torch.empty(2 if B > S else 1, S * lmax, dtype=torch.float32, device=dev)
+        nstages = (B + S - 1) // S
+        fe_main = self.FE_ON_MAIN
+        K = min(nstages, 4 if fe_main else 2)           # device staging slots (the pinned side always has two)
+        dwave = torch.empty(K, S * lmax, dtype=torch.float32, device=dev)
         scratch = torch.empty(max(int(lib.vp_frontend_scratch_floats(eng.handle, S, lmax)), 1), dtype=torch.float32, device=dev)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
         cs = self._copy_stream
         cs_ptr = C.c_void_p(cs.cuda_stream)
         main = torch.cuda.current_stream(dev)
+        fs = main if fe_main else cs                    # stream of the front-end kernels
+        fs_ptr = C.c_void_p(fs.cuda_stream)
         cs.wait_stream(main)                            # buffers handed out by the allocator may still be in use on main
         ptrs = np.fromiter((w.__array_interface__['data'][0] for w in waves), dtype=np.uint64, count=B)
         lens = np.fromiter((w.shape[0] for w in waves), dtype=np.int32, count=B)
         nthreads = self._gather_threads()
         mark('host prep done (keep, buffers, pointer table)')
+        dtr = self._trace_dev                           # None, or a list for (label, timing event) pairs
+
+        def dmark(label, stream):
+            if dtr is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                dtr.append((label, e))
+        dmark('t0 (main stream)', main)
         fe_fn = lib.vp_fbank if desc.kind == 0 else (lib.vp_mfcc if desc.post == 1 else lib.vp_melspec)
-        free_ev = [None, None]                          # front-end finished reading device slot / pinned slot reusable
+        pin_ev = [None, None]                           # H2D copies out of a pinned slot finished: the host may refill it
+        dev_ev = [None] * K                             # front-end finished reading a device slot: the copies may refill it
         next_chunk = 0
         for gi, g0 in enumerate(range(0, B, S)):
             g1 = min(g0 + S, B)
             n = g1 - g0
-            slot = gi & 1
-            if free_ev[slot] is not None:
-                free_ev[slot].synchronize()
-            host = self._pinned_slot(slot, n * lmax)
-            dw = dwave[slot]
+            ps, ds = gi & 1, gi % K
+            if pin_ev[ps] is not None:
+                pin_ev[ps].synchronize()
+            if dev_ev[ds] is not None:
+                cs.wait_event(dev_ev[ds])
+            host = self._pinned_slot(ps, n * lmax)
+            dw = dwave[ds]
             rc = lib.vp_host_stage_h2d(C.c_void_p(ptrs.ctypes.data + 8 * g0), C.c_void_p(lens.ctypes.data + 4 * g0), n, lmax,
                                        C.c_void_p(host.data_ptr()), C.c_void_p(dw.data_ptr()), self.COPY_SLICE, nthreads, cs_ptr)
             if rc != L.VP_OK:
                 raise L.VpError(rc, 'vp_host_stage_h2d failed')
             mark(f'stage {gi}: {n} utterances gathered, H2D enqueued')
+            cev = torch.cuda.Event()
+            cev.record(cs)
+            pin_ev[ps] = cev
+            dmark(f'stage {gi}: H2D done', cs)
+            if fe_main:
+                main.wait_event(cev)
             kp = C.c_void_p(keep_all.data_ptr() + 4 * g0) if keep_all is not None else C.c_void_p()
             if whole and group is not None:
-                fz.mfcc_sharded(dw, n, lmax, kp, feats, scratch, cs, group)
+                fz.mfcc_sharded(dw, n, lmax, kp, feats, scratch, fs, group)
             else:
                 from .engine import _check
                 _check(eng.handle, fe_fn(eng.handle, C.c_void_p(dw.data_ptr()), n, lmax, kp,
-                                         C.c_void_p(feats.data_ptr() + 4 * g0 * T * F), C.c_void_p(scratch.data_ptr()), cs_ptr))
-            ev = torch.cuda.Event()
-            ev.record(cs)
-            free_ev[slot] = ev
+                                         C.c_void_p(feats.data_ptr() + 4 * g0 * T * F), C.c_void_p(scratch.data_ptr()), fs_ptr))
+            fev = torch.cuda.Event()
+            fev.record(fs)
+            dev_ev[ds] = fev
+            dmark(f'stage {gi}: front-end done', fs)
             # backbone chunks whose features are now complete
             while bounds and bounds[0] <= g1:
                 hi = bounds.pop(0)
-                main.wait_event(ev)
+                if not fe_main:
+                    main.wait_event(fev)
                 self.predictor.program(hi - next_chunk, T).run(feats[next_chunk:hi], emb[next_chunk:hi])
+                dmark(f'backbone rows {next_chunk}:{hi} done', main)
                 next_chunk = hi
         # the staging / feature buffers go back to the allocator for the main stream: order the copy stream before that
         main.wait_stream(cs)
