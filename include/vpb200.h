@@ -230,10 +230,10 @@ int vp_device_zero(void* device_ptr, size_t nbytes, void* stream);
 int vp_cosine_scores(vp_handle* h, const float* a, int32_t n, const float* b, int32_t m, int32_t D, float* scores, void* stream);
 
 /* Staging half of predict_batch (predict.py:244-255) as ONE native call: worker threads gather slices of slice_rows
- * utterances into the zero-padded PINNED matrix staging[n, lmax]; the calling thread issues
- * cudaMemcpyAsync(staging slice -> device_dst slice) on copy_stream as soon as a slice is complete, so the H2D transfer
- * of slice k overlaps the gather of slice k+1.  Returns when the last copy has been ENQUEUED.  device_dst == NULL: gather
- * only (== vp_host_gather_pad). */
+ * utterances into the zero-padded PINNED matrix staging[n, lmax]; the calling thread -- one of the n_threads gatherers --
+ * issues cudaMemcpyAsync(staging slice -> device_dst slice) on copy_stream, in slice order, as soon as a slice is
+ * complete, so the H2D transfer of slice k overlaps the gather of slice k+1 (also with n_threads == 1).  Returns when the
+ * last copy has been ENQUEUED.  device_dst == NULL: gather only (== vp_host_gather_pad). */
 int vp_host_stage_h2d(const float* const* srcs, const int32_t* lens, int32_t n, int32_t lmax, float* staging,
                       float* device_dst, int32_t slice_rows, int32_t n_threads, void* copy_stream);
 /* bytes of the handle's shared workspace arena right now */

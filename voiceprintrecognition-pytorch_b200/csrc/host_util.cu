@@ -130,22 +130,13 @@ extern "C" int vp_host_stage_h2d(const float* const* srcs, const int32_t* lens, 
   }
   P->cv_job.notify_all();
   int rc = VP_OK;
-  if (device_dst == nullptr || nt == 1) {
-    P->run_slices();                                   // the caller is a worker too when it has no copies to issue
-  }
-  // hand every slice to the copy engine as soon as it is complete (in order, so the device side can consume prefixes)
-  for (int s = 0; s < n_slices; ++s) {
-    for (int spin = 0; spin < 200000 && !P->done[s].load(std::memory_order_acquire); ++spin) {   // ~ms: slices are short
-#if defined(__x86_64__)
-      __builtin_ia32_pause();
-#endif
-    }
-    if (!P->done[s].load(std::memory_order_acquire)) {
-      std::unique_lock<std::mutex> lk(P->mu);
-      P->cv_done.wait(lk, [&] { return P->done[s].load(std::memory_order_acquire) != 0; });
-    }
+  // The calling thread is a gatherer too (n_threads counts it): between two slices of its own it hands every slice that
+  // is complete -- in order, so the device side can consume prefixes -- to the copy engine.  With n_threads == 1 the call
+  // degenerates to gather slice k / enqueue copy k, still overlapping the H2D of slice k with the gather of slice k+1.
+  int issued = 0;
+  auto issue = [&](int s_) {
     if (device_dst != nullptr && rc == VP_OK) {
-      const int r0 = s * slice_rows, r1 = std::min(n, r0 + slice_rows);
+      const int r0 = s_ * slice_rows, r1 = std::min(n, r0 + slice_rows);
       const size_t off = (size_t)r0 * lmax;
       if (cudaMemcpyAsync(device_dst + off, staging + off, (size_t)(r1 - r0) * lmax * sizeof(float), cudaMemcpyHostToDevice,
                           (cudaStream_t)copy_stream) != cudaSuccess) {
@@ -153,6 +144,26 @@ extern "C" int vp_host_stage_h2d(const float* const* srcs, const int32_t* lens, 
         rc = VP_ERR_CUDA;
       }
     }
+  };
+  for (;;) {
+    while (issued < n_slices && P->done[issued].load(std::memory_order_acquire)) issue(issued++);
+    const int s = P->next.fetch_add(1, std::memory_order_acq_rel);
+    if (s >= n_slices) break;
+    const int r0 = s * slice_rows, r1 = std::min(n, r0 + slice_rows);
+    gather_rows(srcs, lens, lmax, staging, r0, r1);
+    P->done[s].store(1, std::memory_order_release);
+  }
+  for (; issued < n_slices; ++issued) {                // the workers' last slices
+    for (int spin = 0; spin < 200000 && !P->done[issued].load(std::memory_order_acquire); ++spin) {   // ~ms: slices are short
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    if (!P->done[issued].load(std::memory_order_acquire)) {
+      std::unique_lock<std::mutex> lk(P->mu);
+      P->cv_done.wait(lk, [&] { return P->done[issued].load(std::memory_order_acquire) != 0; });
+    }
+    issue(issued);
   }
   {                                                    // the job's memory must not be touched after we return
     std::unique_lock<std::mutex> lk(P->mu);

@@ -185,7 +185,7 @@ class MVectorPredictor:
     #: utterances per staging call (host gather -> pinned -> H2D -> front-end kernels), double buffered
     STAGE_ROWS = int(os.environ.get('VPB_STAGE_ROWS', '128'))
     #: utterances per H2D copy inside a staging call (the copy of slice k overlaps the gather of slice k+1)
-    COPY_SLICE = int(os.environ.get('VPB_COPY_SLICE', '8'))
+    COPY_SLICE = int(os.environ.get('VPB_COPY_SLICE', '4'))
     #: utterances per backbone program on the HOST-staged path: smaller than MAX_BATCH so that the backbone of chunk k runs
     #: while the host gathers and copies chunk k+1 (measured on B200, 256 x 3 s: 7.2 ms with one chunk, 6.4 ms with two)
     HOST_CHUNK = int(os.environ.get('VPB_HOST_CHUNK', '128'))
@@ -208,13 +208,25 @@ class MVectorPredictor:
             local_world = 1          # the launcher already gave this rank its own CPU slice (bind_rank_to_local_cpus)
         per_rank = ncpu // local_world
         quota = MVectorPredictor._cgroup_cpus()
-        if quota is not None:        # a container CPU quota is shared by ALL ranks of the node, bound or not
+        if quota is not None:
+            # a container CPU quota is shared by ALL ranks of the node, bound or not.  Under CFS bandwidth control every
+            # short-lived wake-up of a worker thread also strands up to 1 ms of quota on its core, so many threads per rank
+            # get the whole job throttled (B200 box with a 16-CPU quota, 8 ranks x 8 threads: 10.3 ms per call against 7.3
+            # alone): never more threads than this rank's share
             per_rank = min(per_rank, int(quota // max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))))
-        return max(1, min(8, per_rank - 1))
+        return max(1, min(8, per_rank))                 # the calling thread counts: it gathers between issuing copies
+
+    _quota_cache = []
 
     @staticmethod
     def _cgroup_cpus():
         """CPUs' worth of time the container may use (cgroup v2 cpu.max / v1 cfs quota), or None when unlimited."""
+        if not MVectorPredictor._quota_cache:
+            MVectorPredictor._quota_cache.append(MVectorPredictor._read_cgroup_cpus())
+        return MVectorPredictor._quota_cache[0]
+
+    @staticmethod
+    def _read_cgroup_cpus():
         try:
             with open('/sys/fs/cgroup/cpu.max') as f:
                 q, p = f.read().split()
@@ -302,7 +314,9 @@ class MVectorPredictor:
         F = fz.feature_dim
         keep_all = None
         if masked:
-            keep_all = fz.keep_frames(torch.tensor([w.shape[0] / lmax for w in waves], dtype=torch.float32), T).to(dev)
+            lens64 = np.fromiter(map(len, waves), dtype=np.int64, count=B)
+            # float64 quotient rounded once to float32 == torch.tensor([len / lmax ...], dtype=float32) of predict.py:251-255
+            keep_all = fz.keep_frames(torch.from_numpy((lens64 / lmax).astype(np.float32)), T).to(dev)
         emb = torch.empty(B, D, dtype=torch.float32, device=dev)
         feats = torch.empty(B, T * F, dtype=torch.float32, device=dev)
         bounds = np.cumsum(self._host_chunks(B, T)).tolist()       # end row of every backbone chunk
@@ -321,8 +335,8 @@ class MVectorPredictor:
         fs = main if fe_main else cs                    # stream of the front-end kernels
         fs_ptr = C.c_void_p(fs.cuda_stream)
         cs.wait_stream(main)                            # buffers handed out by the allocator may still be in use on main
-        ptrs = np.fromiter((w.__array_interface__['data'][0] for w in waves), dtype=np.uint64, count=B)
-        lens = np.fromiter((w.shape[0] for w in waves), dtype=np.int32, count=B)
+        ptrs = np.empty(B, dtype=np.uint64)              # filled stage by stage: only stage 0's part is on the critical path
+        lens = np.fromiter(map(len, waves), dtype=np.int32, count=B)
         nthreads = self._gather_threads()
         mark('host prep done (keep, buffers, pointer table)')
         dtr = self._trace_dev                           # None, or a list for (label, timing event) pairs
@@ -347,6 +361,7 @@ class MVectorPredictor:
                 cs.wait_event(dev_ev[ds])
             host = self._pinned_slot(ps, n * lmax)
             dw = dwave[ds]
+            ptrs[g0:g1] = np.fromiter((w.__array_interface__['data'][0] for w in waves[g0:g1]), dtype=np.uint64, count=n)
             rc = lib.vp_host_stage_h2d(C.c_void_p(ptrs.ctypes.data + 8 * g0), C.c_void_p(lens.ctypes.data + 4 * g0), n, lmax,
                                        C.c_void_p(host.data_ptr()), C.c_void_p(dw.data_ptr()), self.COPY_SLICE, nthreads, cs_ptr)
             if rc != L.VP_OK:
