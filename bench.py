@@ -513,7 +513,9 @@ def run_gpu_arm(args, cfg):
                 'e2e': {'value': e2e_v, 'unit': 'emb/s', 'h2d_bytes_per_step': h2d,
                         'd2h_bytes_per_step': n_glob * D * 4, 'ms_per_step': ms_e2e / args.steps,
                         'api': 'mvector.distributed.predict_batch_sharded(MVectorPredictor, list of host float32 arrays) '
-                               '(== MVectorPredictor.predict_batch at 1 GPU)'},
+                               '(== MVectorPredictor.predict_batch at 1 GPU)',
+                        'host': {'cpus_bound': len(bound) if bound else None, 'cgroup_cpu_quota': MVectorPredictor._cgroup_cpus(),
+                                 'gather_threads_per_rank': MVectorPredictor._gather_threads()}},
                 'gpu_launches': args.steps * launches_per_step,
                 'launches_per_step': launches_per_step,
                 'roofline': roof}

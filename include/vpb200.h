@@ -236,6 +236,11 @@ int vp_cosine_scores(vp_handle* h, const float* a, int32_t n, const float* b, in
  * last copy has been ENQUEUED.  device_dst == NULL: gather only (== vp_host_gather_pad). */
 int vp_host_stage_h2d(const float* const* srcs, const int32_t* lens, int32_t n, int32_t lmax, float* staging,
                       float* device_dst, int32_t slice_rows, int32_t n_threads, void* copy_stream);
+/* Process-wide switch of the staging gather: on != 0 -> rows are written with non-temporal (streaming) stores, which skip
+ * the read-for-ownership of the pinned destination lines (the copy engine, not a CPU, reads them next): less DRAM traffic
+ * when several ranks of one host stage at the same time.  Returns 1 when streaming stores are in effect (x86-64 with AVX2
+ * or AVX-512), 0 otherwise (plain memcpy).  on < 0: query only. */
+int vp_host_gather_streaming(int on);
 /* bytes of the handle's shared workspace arena right now */
 size_t vp_workspace_bytes(const vp_handle* h);
 /* number of kernel launches one vp_embed enqueues (bench.py's gpu_launches) */

@@ -214,6 +214,124 @@ def test_host_stage_pool_reuse_slices_and_threads():
                                      dst.ctypes.data_as(C.c_void_p), C.c_void_p(), 0, 2, C.c_void_p()) == L.VP_ERR_INVALID
 
 
+def test_host_stage_copy_path_with_stub_runtime(tmp_path):
+    """The copy-issuing half of vp_host_stage_h2d without a GPU: host_util.cu + host_copy.cpp compiled with g++ against a
+    test double of cuda_runtime.h (tests/stubs: "device" = host memory, cudaMemcpyAsync = memcpy + log).  The copies must
+    tile [0, n * lmax) in order without gaps or overlap (consecutive finished slices may be merged into one copy), the
+    "device" matrix must equal the zero-padded reference for every thread count / slice size / store mode, and a failing
+    copy is reported as VP_ERR_CUDA after the job has drained."""
+    import ctypes as C
+    import subprocess
+    csrc = os.path.join(ROOT, 'voiceprintrecognition-pytorch_b200', 'csrc')
+    so = str(tmp_path / 'libstage_stub.so')
+    cmd = ['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-pthread', '-I', os.path.join(ROOT, 'tests', 'stubs'),
+           '-x', 'c++', os.path.join(csrc, 'host_util.cu'), os.path.join(csrc, 'host_copy.cpp'),
+           os.path.join(ROOT, 'tests', 'stubs', 'stub_runtime.cpp'), '-o', so]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lib = C.CDLL(so)
+    lib.vp_host_stage_h2d.restype = C.c_int
+    lib.vp_host_stage_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.c_void_p]
+    lib.stub_get.argtypes = [C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    rng = np.random.default_rng(3)
+    for trial in range(8):
+        n, lmax = int(rng.integers(1, 150)), int(rng.integers(1, 5000))
+        lens = rng.integers(0, lmax + 1, n).astype(np.int32)
+        lens[int(rng.integers(0, n))] = lmax
+        ws = [rng.standard_normal(max(int(ln), 1)).astype(np.float32) for ln in lens]
+        ptrs = np.fromiter((w.__array_interface__['data'][0] for w in ws), dtype=np.uint64, count=n)
+        ref = np.zeros((n, lmax), dtype=np.float32)
+        for i, w in enumerate(ws):
+            ref[i, :lens[i]] = w[:lens[i]]
+        for streaming in (0, 1):
+            lib.vp_host_gather_streaming(streaming)
+            for threads, slice_rows in ((1, 1), (1, 7), (2, 4), (8, 4), (8, 1), (4, 1000)):
+                staging = np.full((n, lmax), np.nan, dtype=np.float32)
+                device = np.full((n, lmax), np.nan, dtype=np.float32)
+                lib.stub_reset(C.c_void_p(device.ctypes.data), -1)
+                rc = lib.vp_host_stage_h2d(ptrs.ctypes.data, lens.ctypes.data, n, lmax, staging.ctypes.data, device.ctypes.data,
+                                           slice_rows, threads, None)
+                assert rc == 0 and np.array_equal(device, ref) and np.array_equal(staging, ref), (trial, threads, slice_rows)
+                pos, n_slices = 0, (n + slice_rows - 1) // slice_rows
+                assert 1 <= lib.stub_count() <= n_slices
+                for k in range(lib.stub_count()):
+                    off, nb = C.c_size_t(), C.c_size_t()
+                    lib.stub_get(k, C.byref(off), C.byref(nb))
+                    assert off.value == pos and nb.value > 0 and nb.value % (4 * lmax) == 0   # whole rows, in order, no gap
+                    assert (nb.value // (4 * lmax)) % slice_rows == 0 or pos + nb.value == n * lmax * 4
+                    pos += nb.value
+                assert pos == n * lmax * 4
+        # a copy that fails: error code after the job has drained, no hang, later calls work again
+        device = np.zeros((n, lmax), dtype=np.float32)
+        staging = np.zeros((n, lmax), dtype=np.float32)
+        lib.stub_reset(C.c_void_p(device.ctypes.data), 0)
+        assert lib.vp_host_stage_h2d(ptrs.ctypes.data, lens.ctypes.data, n, lmax, staging.ctypes.data, device.ctypes.data,
+                                     2, 3, None) == 2                  # VP_ERR_CUDA
+        assert np.array_equal(staging, ref)
+    lib.vp_host_gather_streaming(0)
+
+
+def test_host_stage_streaming_stores_same_bytes():
+    """vp_host_gather_streaming(1): the gather writes the pinned rows with non-temporal stores (AVX2 / AVX-512 picked at run
+    time).  Same staging matrix as memcpy for every alignment of source and destination, nothing written outside the
+    matrix, and the switch reports whether streaming stores are in effect."""
+    import ctypes as C
+    from mvector import _lib as L
+    lib = L.lib()
+    try:
+        eff = lib.vp_host_gather_streaming(1)
+        assert eff in (0, 1) and lib.vp_host_gather_streaming(-1) == 1
+        rng = np.random.default_rng(11)
+        for trial in range(12):
+            n, lmax = int(rng.integers(1, 60)), int(rng.integers(1, 9000))
+            lens = rng.integers(0, lmax + 1, n).astype(np.int32)
+            lens[int(rng.integers(0, n))] = lmax
+            ws = []
+            for ln in lens:                              # sources at odd float offsets inside their allocations
+                off = int(rng.integers(0, 17))
+                base = rng.standard_normal(int(ln) + off + 1).astype(np.float32)
+                ws.append(base[off:off + int(ln)] if ln > 0 else base[:1])
+            ptrs = np.fromiter((w.__array_interface__['data'][0] for w in ws), dtype=np.uint64, count=n)
+            ref = np.zeros((n, lmax), dtype=np.float32)
+            for i, w in enumerate(ws):
+                ref[i, :lens[i]] = w[:lens[i]]
+            for threads, slice_rows in ((1, 1), (2, 4), (8, 3), (3, 100)):
+                o = int(rng.integers(0, 16))             # destination at every 4-byte phase of a cache line
+                buf = np.full(n * lmax + 16, 7.0, dtype=np.float32)
+                dst = buf[o:o + n * lmax].reshape(n, lmax)
+                rc = lib.vp_host_stage_h2d(C.c_void_p(ptrs.ctypes.data), C.c_void_p(lens.ctypes.data), n, lmax,
+                                           C.c_void_p(dst.ctypes.data), C.c_void_p(), slice_rows, threads, C.c_void_p())
+                assert rc == 0 and np.array_equal(dst, ref), (trial, threads, slice_rows)
+                assert (buf[:o] == 7.0).all() and (buf[o + n * lmax:] == 7.0).all()
+    finally:
+        lib.vp_host_gather_streaming(0)
+    assert lib.vp_host_gather_streaming(-1) == 0
+
+
+def test_gather_threads_follow_affinity_world_and_cpu_quota(monkeypatch):
+    """Staging threads per rank: the process's CPUs split between the ranks of the node, never more than the rank's share
+    of a container CPU quota (cgroup), 8 at most, the env override wins."""
+    import os
+    from mvector.predict import MVectorPredictor as P
+    monkeypatch.delenv('VPB_GATHER_THREADS', raising=False)
+    monkeypatch.setattr(os, 'sched_getaffinity', lambda pid: set(range(128)), raising=False)
+    monkeypatch.setattr(os, 'cpu_count', lambda: 128)
+    for quota, world, want in ((None, 1, 8), (None, 8, 8), (16.0, 1, 8), (16.0, 8, 2), (16.0, 4, 4), (4.0, 8, 1), (None, 64, 2)):
+        monkeypatch.setattr(P, '_quota_cache', [quota])
+        monkeypatch.setenv('LOCAL_WORLD_SIZE', str(world))
+        assert P._gather_threads() == want, (quota, world)
+    # a rank already bound to its own slice (bind_rank_to_local_cpus): the slice is not divided again, the quota still is
+    monkeypatch.setattr(os, 'sched_getaffinity', lambda pid: set(range(16)), raising=False)
+    monkeypatch.setattr(P, '_quota_cache', [None])
+    monkeypatch.setenv('LOCAL_WORLD_SIZE', '8')
+    assert P._gather_threads() == 8
+    monkeypatch.setattr(P, '_quota_cache', [16.0])
+    assert P._gather_threads() == 2
+    monkeypatch.setenv('VPB_GATHER_THREADS', '5')
+    assert P._gather_threads() == 5
+
+
 def test_metrics_match_reference_golden():
     """mvector.metric.metrics (metrics.py:5-39) against outputs of the reference's own functions on seeded scores with
     ties (tests/golden/metrics.npz): fnr / fpr / thresholds bit-exact, EER / threshold / minDCF to 1e-12."""

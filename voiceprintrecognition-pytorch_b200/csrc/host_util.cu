@@ -16,12 +16,21 @@
 
 namespace {
 
-inline void gather_rows(const float* const* srcs, const int32_t* lens, int lmax, float* dst, int r0, int r1) {
+// host_copy.cpp: non-temporal row copy (run-time AVX dispatch) and the store fence that must precede publication
+extern "C" int vpb_copy_stream_level();
+extern "C" void vpb_copy_stream(float* dst, const float* src, size_t n);
+extern "C" void vpb_copy_stream_fence();
+
+std::atomic<int> g_streaming{0};   // vp_host_gather_streaming: 1 = gather with streaming stores
+
+inline void gather_rows(const float* const* srcs, const int32_t* lens, int lmax, float* dst, int r0, int r1, bool streaming) {
   for (int i = r0; i < r1; ++i) {
     float* row = dst + (size_t)i * lmax;
-    std::memcpy(row, srcs[i], (size_t)lens[i] * sizeof(float));
+    if (streaming) vpb_copy_stream(row, srcs[i], (size_t)lens[i]);
+    else std::memcpy(row, srcs[i], (size_t)lens[i] * sizeof(float));
     if (lens[i] < lmax) std::memset(row + lens[i], 0, (size_t)(lmax - lens[i]) * sizeof(float));
   }
+  if (streaming) vpb_copy_stream_fence();   // before the slice's done flag: the copy engine reads these rows next
 }
 
 // Persistent worker pool (created on first use, never joined: the workers sleep on a condition variable and die with the
@@ -37,6 +46,7 @@ struct Pool {
   const int32_t* lens = nullptr;
   float* dst = nullptr;
   int n = 0, lmax = 0, slice_rows = 0, n_slices = 0;
+  bool streaming = false;
   std::atomic<int> next{0};
   std::vector<std::atomic<int>> done;      // per slice: 1 when gathered
   int remaining = 0;                       // participating workers that have not finished the current job yet
@@ -48,7 +58,7 @@ struct Pool {
       const int s = next.fetch_add(1, std::memory_order_acq_rel);
       if (s >= n_slices) break;
       const int r0 = s * slice_rows, r1 = std::min(n, r0 + slice_rows);
-      gather_rows(srcs, lens, lmax, dst, r0, r1);
+      gather_rows(srcs, lens, lmax, dst, r0, r1, streaming);
       done[s].store(1, std::memory_order_release);
       { std::lock_guard<std::mutex> lk(mu); }
       cv_done.notify_all();
@@ -99,6 +109,13 @@ std::mutex g_job_mu;               // one staging job at a time per process
 
 }  // namespace
 
+extern "C" int vp_host_gather_streaming(int on) {
+  if (on < 0) return g_streaming.load(std::memory_order_relaxed);
+  const int prev = g_streaming.exchange(on ? 1 : 0, std::memory_order_relaxed);
+  (void)prev;
+  return (on && vpb_copy_stream_level() > 0) ? 1 : 0;
+}
+
 extern "C" int vp_host_gather_pad(const float* const* srcs, const int32_t* lens, int32_t n, int32_t lmax, float* dst,
                                   int32_t n_threads) {
   return vp_host_stage_h2d(srcs, lens, n, lmax, dst, nullptr, n > 0 ? (n + std::max(1, n_threads) - 1) / std::max(1, n_threads) : 1,
@@ -115,12 +132,14 @@ extern "C" int vp_host_stage_h2d(const float* const* srcs, const int32_t* lens, 
   if (n_slices > 4096) return VP_ERR_INVALID;
   const int nt = std::max(1, std::min<int>(std::min<int>(n_threads, n_slices), 32));
   std::lock_guard<std::mutex> job(g_job_mu);
+  const bool streaming = g_streaming.load(std::memory_order_relaxed) != 0 && vpb_copy_stream_level() > 0;
   Pool* P = pool();
   {
     std::lock_guard<std::mutex> lk(P->mu);
     P->ensure(nt - 1);
     P->srcs = srcs; P->lens = lens; P->dst = staging; P->n = n; P->lmax = lmax;
     P->slice_rows = slice_rows; P->n_slices = n_slices;
+    P->streaming = streaming;
     for (int s = 0; s < n_slices; ++s) P->done[s].store(0, std::memory_order_relaxed);
     P->next.store(0, std::memory_order_release);
     P->want_workers = nt - 1;
@@ -133,10 +152,16 @@ extern "C" int vp_host_stage_h2d(const float* const* srcs, const int32_t* lens, 
   // The calling thread is a gatherer too (n_threads counts it): between two slices of its own it hands every slice that
   // is complete -- in order, so the device side can consume prefixes -- to the copy engine.  With n_threads == 1 the call
   // degenerates to gather slice k / enqueue copy k, still overlapping the H2D of slice k with the gather of slice k+1.
+  // Consecutive finished slices go out as ONE copy: when enqueueing is cheap the copies stay fine grained (first bytes on
+  // the bus early), when it is slow -- eight ranks of one host in the driver at once: tens of us per call -- more slices
+  // finish meanwhile and the copies grow by themselves.
   int issued = 0;
-  auto issue = [&](int s_) {
+  auto issue_ready = [&]() {
+    int j = issued;
+    while (j < n_slices && P->done[j].load(std::memory_order_acquire)) ++j;
+    if (j == issued) return;
     if (device_dst != nullptr && rc == VP_OK) {
-      const int r0 = s_ * slice_rows, r1 = std::min(n, r0 + slice_rows);
+      const int r0 = issued * slice_rows, r1 = std::min(n, j * slice_rows);
       const size_t off = (size_t)r0 * lmax;
       if (cudaMemcpyAsync(device_dst + off, staging + off, (size_t)(r1 - r0) * lmax * sizeof(float), cudaMemcpyHostToDevice,
                           (cudaStream_t)copy_stream) != cudaSuccess) {
@@ -144,16 +169,17 @@ extern "C" int vp_host_stage_h2d(const float* const* srcs, const int32_t* lens, 
         rc = VP_ERR_CUDA;
       }
     }
+    issued = j;
   };
   for (;;) {
-    while (issued < n_slices && P->done[issued].load(std::memory_order_acquire)) issue(issued++);
+    issue_ready();
     const int s = P->next.fetch_add(1, std::memory_order_acq_rel);
     if (s >= n_slices) break;
     const int r0 = s * slice_rows, r1 = std::min(n, r0 + slice_rows);
-    gather_rows(srcs, lens, lmax, staging, r0, r1);
+    gather_rows(srcs, lens, lmax, staging, r0, r1, streaming);
     P->done[s].store(1, std::memory_order_release);
   }
-  for (; issued < n_slices; ++issued) {                // the workers' last slices
+  while (issued < n_slices) {                          // the workers' last slices
     for (int spin = 0; spin < 200000 && !P->done[issued].load(std::memory_order_acquire); ++spin) {   // ~ms: slices are short
 #if defined(__x86_64__)
       __builtin_ia32_pause();
@@ -163,7 +189,7 @@ extern "C" int vp_host_stage_h2d(const float* const* srcs, const int32_t* lens, 
       std::unique_lock<std::mutex> lk(P->mu);
       P->cv_done.wait(lk, [&] { return P->done[issued].load(std::memory_order_acquire) != 0; });
     }
-    issue(issued);
+    issue_ready();
   }
   {                                                    // the job's memory must not be touched after we return
     std::unique_lock<std::mutex> lk(P->mu);

@@ -192,7 +192,18 @@ class MVectorPredictor:
     # front-end kernels on the main stream, right before their backbone chunk (1), or on the copy stream behind their data (0,
     # where they sit between two stages' H2D copies and hold the second one up)
     FE_ON_MAIN = os.environ.get('VPB_FE_STREAM', 'main') == 'main'
+    #: staging gather with non-temporal stores: '1' / '0', or 'auto' = only when several ranks share this host (their
+    #: gathers run at the same time and are DRAM-bound; the single-process path keeps the measured memcpy gather)
+    GATHER_NT = os.environ.get('VPB_GATHER_NT', 'auto')
+    _gather_configured = False
     WS_LIMIT_BYTES = int(float(os.environ.get('VPB_WS_LIMIT_GB', '64')) * 2 ** 30)
+
+    @classmethod
+    def _configure_gather(cls, lib):
+        if not cls._gather_configured:
+            on = cls.GATHER_NT == '1' or (cls.GATHER_NT == 'auto' and int(os.environ.get('LOCAL_WORLD_SIZE', '1')) > 1)
+            lib.vp_host_gather_streaming(1 if on else 0)
+            cls._gather_configured = True
 
     @staticmethod
     def _gather_threads():
@@ -338,6 +349,7 @@ class MVectorPredictor:
         ptrs = np.empty(B, dtype=np.uint64)              # filled stage by stage: only stage 0's part is on the critical path
         lens = np.fromiter(map(len, waves), dtype=np.int32, count=B)
         nthreads = self._gather_threads()
+        self._configure_gather(lib)
         mark('host prep done (keep, buffers, pointer table)')
         dtr = self._trace_dev                           # None, or a list for (label, timing event) pairs
 
