@@ -395,6 +395,51 @@ def run_gpu_arm(args, cfg):
     dis = float(((e_res - e_host).norm(dim=1) / e_res.norm(dim=1)).max())
     assert dis <= 2e-6, f'resident and host-staged paths disagree: rel-L2 {dis}'
 
+    # ---- SURVEY 8(d)'s other end-to-end starting point: the shard already zero padded in ONE pinned host matrix (what a
+    # serving stack with its own staging hands over).  H2D of the matrix in backbone-chunk pieces on a copy stream, the
+    # product's device entry point (embed_device) behind each piece, all-gather, D2H.  Reported beside `e2e`, never instead.
+    pinned = None
+    try:
+        whole_fe = fz.feat_fun.desc.post == 1 and fz.feat_fun.desc.top_db >= 0      # MFCC: the clamp spans the call
+        pins = [p['dev'].cpu().pin_memory() for p in pools]
+        stage = [torch.empty_like(p['dev']) for p in pools]
+        cstream = torch.cuda.Stream(device=dev)
+
+        def step_pinned(i):
+            k = i % N_POOL
+            p, src, dst = pools[k], pins[k], stage[k]
+            cuts = [B] if whole_fe else pred._host_chunks(B, fz.num_frames(p['lmax']))
+            main = torch.cuda.current_stream(dev)
+            cstream.wait_stream(main)
+            evs, r = [], 0
+            with torch.cuda.stream(cstream):
+                for c in cuts:
+                    dst[r:r + c].copy_(src[r:r + c], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cstream)
+                    evs.append(ev)
+                    r += c
+            outs, r = [], 0
+            for c, ev in zip(cuts, evs):
+                main.wait_event(ev)
+                outs.append(pred.embed_device(dst[r:r + c], lens=p['lens'][lo + r:lo + r + c] if cfg['ragged'] else None))
+                r += c
+            loc = outs[0] if len(outs) == 1 else torch.cat(outs)
+            return mdist.gather_embeddings(loc, n_glob, out=emb_all).cpu()
+
+        ms_pin = timed(step_pinned, args.steps, max(args.warmup, 3))
+        e_pin = step_pinned(i_chk).to(dev)
+        sync_all()
+        dis_pin = float(((e_res - e_pin).norm(dim=1) / e_res.norm(dim=1)).max())
+        pinned = {'value': n_glob * args.steps / (ms_pin * 1e-3), 'unit': 'emb/s', 'ms_per_step': ms_pin / args.steps,
+                  'max_rel_l2_vs_resident': dis_pin,
+                  'input': 'per rank one zero-padded pinned float32 [B/R, Lmax] matrix (no host gather)',
+                  'api': 'cudaMemcpyAsync pieces + MVectorPredictor.embed_device + gather_embeddings + D2H'}
+        del pins, stage
+        mark(f'pinned-matrix e2e done: {ms_pin:.2f} ms')
+    except Exception as e:                               # an extra figure: never takes the bench line down with it
+        pinned = {'error': f'{type(e).__name__}: {e}'[:200]}
+
     T0 = fz.num_frames(lmax0)
     cb = pred._chunk_size(B, T0)
     prog = pred.predictor.program(cb, T0)
@@ -515,7 +560,8 @@ def run_gpu_arm(args, cfg):
                         'api': 'mvector.distributed.predict_batch_sharded(MVectorPredictor, list of host float32 arrays) '
                                '(== MVectorPredictor.predict_batch at 1 GPU)',
                         'host': {'cpus_bound': len(bound) if bound else None, 'cgroup_cpu_quota': MVectorPredictor._cgroup_cpus(),
-                                 'gather_threads_per_rank': MVectorPredictor._gather_threads()}},
+                                 'gather_threads_per_rank': MVectorPredictor._gather_threads()},
+                        'from_pinned_matrix': pinned},
                 'gpu_launches': args.steps * launches_per_step,
                 'launches_per_step': launches_per_step,
                 'roofline': roof}
