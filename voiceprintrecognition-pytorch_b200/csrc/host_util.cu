@@ -110,10 +110,8 @@ std::mutex g_job_mu;               // one staging job at a time per process
 }  // namespace
 
 extern "C" int vp_host_gather_streaming(int on) {
-  if (on < 0) return g_streaming.load(std::memory_order_relaxed);
-  const int prev = g_streaming.exchange(on ? 1 : 0, std::memory_order_relaxed);
-  (void)prev;
-  return (on && vpb_copy_stream_level() > 0) ? 1 : 0;
+  if (on >= 0) g_streaming.store(on ? 1 : 0, std::memory_order_relaxed);
+  return (g_streaming.load(std::memory_order_relaxed) != 0 && vpb_copy_stream_level() > 0) ? 1 : 0;
 }
 
 extern "C" int vp_host_gather_pad(const float* const* srcs, const int32_t* lens, int32_t n, int32_t lmax, float* dst,
