@@ -189,8 +189,8 @@ class MVectorPredictor:
     #: utterances per backbone program on the HOST-staged path: smaller than MAX_BATCH so that the backbone of chunk k runs
     #: while the host gathers and copies chunk k+1 (measured on B200, 256 x 3 s: 7.2 ms with one chunk, 6.4 ms with two)
     HOST_CHUNK = int(os.environ.get('VPB_HOST_CHUNK', '128'))
-    # front-end kernels on the main stream, right before their backbone chunk (1), or on the copy stream behind their data (0,
-    # where they sit between two stages' H2D copies and hold the second one up)
+    #: front-end kernels on the main stream right before their backbone chunk ('main'), or on the copy stream behind their
+    #: data ('copy': there they sit between two stages' H2D copies and hold the second one up)
     FE_ON_MAIN = os.environ.get('VPB_FE_STREAM', 'main') == 'main'
     #: staging gather with non-temporal stores: '1' / '0', or 'auto' = only when several ranks share this host (their
     #: gathers run at the same time and are DRAM-bound; the single-process path keeps the measured memcpy gather)
@@ -299,10 +299,11 @@ class MVectorPredictor:
         mean follow that padded length, frames >= round(len/Lmax * T) are zeroed.
 
         Pipeline (every op is per-utterance, so slicing the batch cannot change results): staging calls of STAGE_ROWS
-        utterances -- native worker threads gather them into pinned memory and the H2D copies are issued slice by slice
-        (``vp_host_stage_h2d``) -- are double buffered against the fused front-end kernels, which run on the copy stream right
-        behind their data and write straight into the [B, T, F] feature buffer; as soon as the features of a backbone
-        chunk (<= MAX_BATCH utterances) are complete the main stream runs its program.  One D2H of the result at the end."""
+        utterances -- native threads gather them into pinned memory and the H2D copies are issued on the copy stream as
+        slices finish (``vp_host_stage_h2d``) -- feed the fused front-end kernels, which run on the main stream behind an
+        event of their stage's copies and write straight into the [B, T, F] feature buffer; as soon as the features of a
+        backbone chunk (``_host_chunks``) are complete the main stream runs its program, under the next stage's gather and
+        copies.  One D2H of the result at the end.  (``VPB_FE_STREAM=copy``: front-end kernels on the copy stream.)"""
         from . import _lib as L
         import ctypes as C
         import time
