@@ -404,6 +404,7 @@ def run_gpu_arm(args, cfg):
         pins = [p['dev'].cpu().pin_memory() for p in pools]
         stage = [torch.empty_like(p['dev']) for p in pools]
         cstream = torch.cuda.Stream(device=dev)
+        loc_pin = torch.empty(B, D, dtype=torch.float32, device=dev)
 
         def step_pinned(i):
             k = i % N_POOL
@@ -419,13 +420,12 @@ def run_gpu_arm(args, cfg):
                     ev.record(cstream)
                     evs.append(ev)
                     r += c
-            outs, r = [], 0
+            r = 0
             for c, ev in zip(cuts, evs):
                 main.wait_event(ev)
-                outs.append(pred.embed_device(dst[r:r + c], lens=p['lens'][lo + r:lo + r + c] if cfg['ragged'] else None))
+                pred.embed_device(dst[r:r + c], lens=p['lens'][lo + r:lo + r + c] if cfg['ragged'] else None, out=loc_pin[r:r + c])
                 r += c
-            loc = outs[0] if len(outs) == 1 else torch.cat(outs)
-            return mdist.gather_embeddings(loc, n_glob, out=emb_all).cpu()
+            return mdist.gather_embeddings(loc_pin, n_glob, out=emb_all).cpu()
 
         ms_pin = timed(step_pinned, args.steps, max(args.warmup, 3))
         e_pin = step_pinned(i_chk).to(dev)

@@ -77,6 +77,8 @@ def test_baseline_config_full_batch_vs_oracle(name):
     xd = torch.from_numpy(x).cuda()
     e_dev = pred.embed_device(xd, lens)
     assert torch.equal(pred.embed_device(xd, lens), e_dev)                   # deterministic (no float atomics on the path)
+    into = torch.empty_like(e_dev)
+    assert pred.embed_device(xd, lens, out=into) is into and torch.equal(into, e_dev)   # caller-owned output rows
     # host-staged vs device-resident: the same kernels on the same data.  With the same backbone chunking they agree bit
     # for bit; the default host path uses smaller chunks (to overlap staging with compute), and a chunk's fp16-split
     # activation scale is a property of the tensor the kernel sees, so the default agrees to a few ulp

@@ -412,12 +412,12 @@ class MVectorPredictor:
         mark('result on host' if to_numpy else 'returned device tensor')
         return out
 
-    def embed_device(self, wave_dev, lens=None, lmax=None, keep=None, group=None):
+    def embed_device(self, wave_dev, lens=None, lmax=None, keep=None, group=None, out=None):
         """Device-resident twin of ``predict_batch``'s compute half: ``wave_dev`` is a CUDA float32 ``[B, Lmax]`` matrix,
         zero padded to the longest item of the (global) batch; ``lens`` the true sample counts (None: every row is full
         length, i.e. no masking) or ``keep`` the precomputed device int32 mask lengths.  Returns the device tensor
-        ``[B, embd_dim]``.  One fused ``vp_embed_wave`` (front-end + backbone) per chunk of <= MAX_BATCH utterances; nothing
-        is copied or synchronised."""
+        ``[B, embd_dim]`` (``out`` when given: a contiguous CUDA float32 ``[B, embd_dim]`` view to write into).  One fused
+        ``vp_embed_wave`` (front-end + backbone) per chunk of <= MAX_BATCH utterances; nothing is copied or synchronised."""
         from . import _lib as L
         assert wave_dev.is_cuda and wave_dev.dtype == torch.float32 and wave_dev.dim() == 2 and wave_dev.is_contiguous()
         B, Lp = wave_dev.shape
@@ -428,7 +428,9 @@ class MVectorPredictor:
         if keep is None and lens is not None:
             keep = fz.keep_frames(torch.tensor([n / Lp for n in lens], dtype=torch.float32), T).to(wave_dev.device)
         D, F = self.predictor.embd_dim, fz.feature_dim
-        emb = torch.empty(B, D, dtype=torch.float32, device=wave_dev.device)
+        if out is not None:
+            assert out.is_cuda and out.dtype == torch.float32 and tuple(out.shape) == (B, D) and out.is_contiguous()
+        emb = out if out is not None else torch.empty(B, D, dtype=torch.float32, device=wave_dev.device)
         cb = self._chunk_size(B, T)
         if desc.post == 1 and desc.top_db >= 0:         # MFCC: call-wide clamp -> front-end on the whole batch first
             feats = fz.forward_keep(wave_dev, keep, group=group)
