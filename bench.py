@@ -398,14 +398,19 @@ def run_gpu_arm(args, cfg):
     # ---- SURVEY 8(d)'s other end-to-end starting point: the shard already zero padded in ONE pinned host matrix (what a
     # serving stack with its own staging hands over).  H2D of the matrix in backbone-chunk pieces on a copy stream, the
     # product's device entry point (embed_device) behind each piece, all-gather, D2H.  Reported beside `e2e`, never instead.
-    pinned = None
-    try:
+    pinned, pin_err = None, None
+    try:                                                 # set-up (pinned allocations) may fail on one rank only ...
         whole_fe = fz.feat_fun.desc.post == 1 and fz.feat_fun.desc.top_db >= 0      # MFCC: the clamp spans the call
         pins = [p['dev'].cpu().pin_memory() for p in pools]
         stage = [torch.empty_like(p['dev']) for p in pools]
         cstream = torch.cuda.Stream(device=dev)
         loc_pin = torch.empty(B, D, dtype=torch.float32, device=dev)
-
+    except Exception as e:
+        pin_err = f'{type(e).__name__}: {e}'[:200]
+    ok = torch.tensor([0 if pin_err else 1], device=dev)
+    if world > 1:                                        # ... so the ranks agree before anyone enters a collective
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 1:
         def step_pinned(i):
             k = i % N_POOL
             p, src, dst = pools[k], pins[k], stage[k]
@@ -427,18 +432,21 @@ def run_gpu_arm(args, cfg):
                 r += c
             return mdist.gather_embeddings(loc_pin, n_glob, out=emb_all).cpu()
 
-        ms_pin = timed(step_pinned, args.steps, max(args.warmup, 3))
-        e_pin = step_pinned(i_chk).to(dev)
-        sync_all()
-        dis_pin = float(((e_res - e_pin).norm(dim=1) / e_res.norm(dim=1)).max())
-        pinned = {'value': n_glob * args.steps / (ms_pin * 1e-3), 'unit': 'emb/s', 'ms_per_step': ms_pin / args.steps,
-                  'max_rel_l2_vs_resident': dis_pin,
-                  'input': 'per rank one zero-padded pinned float32 [B/R, Lmax] matrix (no host gather)',
-                  'api': 'cudaMemcpyAsync pieces + MVectorPredictor.embed_device + gather_embeddings + D2H'}
+        try:                                             # an extra figure: a (rank-symmetric) failure must not take the line down
+            ms_pin = timed(step_pinned, args.steps, max(args.warmup, 3))
+            e_pin = step_pinned(i_chk).to(dev)
+            sync_all()
+            dis_pin = float(((e_res - e_pin).norm(dim=1) / e_res.norm(dim=1)).max())
+            pinned = {'value': n_glob * args.steps / (ms_pin * 1e-3), 'unit': 'emb/s', 'ms_per_step': ms_pin / args.steps,
+                      'max_rel_l2_vs_resident': dis_pin,
+                      'input': 'per rank one zero-padded pinned float32 [B/R, Lmax] matrix (no host gather)',
+                      'api': 'cudaMemcpyAsync pieces + MVectorPredictor.embed_device + gather_embeddings + D2H'}
+            mark(f'pinned-matrix e2e done: {ms_pin:.2f} ms')
+        except Exception as e:
+            pinned = {'error': f'{type(e).__name__}: {e}'[:200]}
         del pins, stage
-        mark(f'pinned-matrix e2e done: {ms_pin:.2f} ms')
-    except Exception as e:                               # an extra figure: never takes the bench line down with it
-        pinned = {'error': f'{type(e).__name__}: {e}'[:200]}
+    else:
+        pinned = {'error': pin_err or 'set-up failed on another rank'}
 
     T0 = fz.num_frames(lmax0)
     cb = pred._chunk_size(B, T0)
